@@ -1,0 +1,151 @@
+/*
+ * mpx.h -- C ABI of the B200-native collocation-transcription hot path of mpopt.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * The reference (pure Python over CasADi, /root/reference/mpopt/mpopt.py) has no FFI
+ * of its own; each entry point below names the reference interface it replaces.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - all values are float64, all indices int64 (CasADi's casadi_int), row/col 0-based;
+ *   - decision vector z, parameters p (segment-width fractions), constraints g and the
+ *     Jacobian follow the reference's layout exactly (mpopt.py:537-543, :631, :458,
+ *     :617-621); the Jacobian is CSR with sorted column indices (CCS adapter provided);
+ *   - every function returns 0 on success, a negative MPX_E* code otherwise and never
+ *     throws; mpx_last_error() gives the message of the last failure on this thread;
+ *   - host-pointer entry points copy z/p to the device, run the kernels, copy results
+ *     back; *_dev entry points take device pointers and a cudaStream_t (as void*) and
+ *     do no host work beyond the launch;
+ *   - a plan owns its device buffers and one CUDA stream; entry points are not
+ *     re-entrant on the same plan, different plans may be used concurrently.
+ *   - there is NO CPU fallback: without a CUDA device mpx_plan_create fails with
+ *     MPX_ENODEVICE.
+ */
+#ifndef MPX_H_
+#define MPX_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPX_VERSION 100
+
+#define MPX_OK 0
+#define MPX_EINVAL (-1)    /* bad argument / inconsistent description           */
+#define MPX_ENODEVICE (-2) /* no usable CUDA device                             */
+#define MPX_ECUDA (-3)     /* CUDA runtime / driver / NVRTC failure             */
+#define MPX_ENOPROGRAM (-4)/* no compiled node functors for this problem        */
+#define MPX_ELIMIT (-5)    /* problem exceeds a compiled-in limit (smem, sizes) */
+
+/* Collocation schemes: CollocationRoots.get_collocation_points, mpopt.py:4157-4188 */
+#define MPX_LGR 0
+#define MPX_LGL 1
+#define MPX_CGL 2
+
+#define MPX_MAX_DIM 16 /* max of n_states, n_controls, n_params, path rows per node */
+
+/* One phase of the OCP: structural information obtained by tracing the user's Python
+ * callables once (what CasADi's SX graph + AD sparsity give the reference at mpopt.py:757).
+ * Pattern matrices are uint8, row-major. Node variables are ordered x_0.., u_0.., a_0..;
+ * terminal variables xf_0.., x0_0.., tf, t0, a_0.. */
+typedef struct mpx_phase_desc {
+  int32_t n_path;          /* path-constraint rows per node (0: none), mpopt.py:239-262    */
+  int32_t n_term;          /* terminal-constraint rows, mpopt.py:264-300                   */
+  const uint8_t* pat_f;    /* [nx][nx+nu+na]   d f_s / d var  structurally nonzero         */
+  const uint8_t* f_nz;     /* [nx]             f_s is not identically zero                 */
+  const uint8_t* f_t;      /* [nx]             f_s depends on t                            */
+  const uint8_t* pat_c;    /* [n_path][nx+nu+na]                                           */
+  const uint8_t* c_t;      /* [n_path]                                                     */
+  const uint8_t* pat_tc;   /* [n_term][2nx+2+na]                                           */
+  int32_t diff_u;          /* control-slope rows present, mpopt.py:302-328                 */
+  int32_t midu;            /* mid-point control rows present, mpopt.py:330-377             */
+  int32_t du_continuity;   /* slope-continuity rows present (needs n_segments>1), :379-413 */
+  int32_t cost_t;          /* running cost depends on t explicitly                         */
+} mpx_phase_desc;
+
+typedef struct mpx_problem_desc {
+  int32_t nx, nu, na, n_phases;
+  const mpx_phase_desc* phases;   /* [n_phases]                                            */
+  int32_t n_segments;             /* per phase, mpopt.py:70                                */
+  const int32_t* poly_orders;     /* [n_segments], shared by all phases, mpopt.py:73-75    */
+  int32_t scheme;                 /* MPX_LGR / MPX_LGL / MPX_CGL                           */
+  double tau_min, tau_max;        /* CollocationRoots._TAU_MIN/_TAU_MAX, mpopt.py:4144-4145*/
+  const double* scale_x;          /* [nx]  OCP.scale_x, mpopt.py:3445-3448                 */
+  const double* scale_u;          /* [nu]                                                  */
+  const double* scale_a;          /* [na]                                                  */
+  double scale_t;
+  int32_t n_links;                /* phase links, mpopt.py:464-521                         */
+  const int32_t* links;           /* [n_links][2] = (phase_i, phase_j)                     */
+  int32_t drop_exact_zeros;       /* SX folds 0*x: exact-zero table entries leave the pattern */
+  const char* program_key;        /* key of the AOT-compiled node functors (may be NULL)   */
+  const char* program_source;     /* generated CUDA source of the node functors for the
+                                     NVRTC path (may be NULL if program_key is registered) */
+  int32_t device;                 /* CUDA device ordinal                                   */
+  int32_t seg_begin, seg_end;     /* shard: evaluate segments [seg_begin, seg_end) of every
+                                     phase; 0,0 means all. Tail rows (terminal, events)
+                                     belong to the shard that owns the last segment.       */
+} mpx_problem_desc;
+
+typedef struct mpx_plan mpx_plan;
+
+int mpx_version(void);
+const char* mpx_last_error(void);
+
+/* -- collocation tables: replaces CollocationRoots._taus_fn, Collocation.get_diff_matrix,
+ *    get_quadrature_weights, get_interpolation_matrix (mpopt.py:4208-4276, :3815-3905).
+ *    Computed on the device. roots[deg+1], D[(deg+1)^2] row-major, w[deg+1] (integral over
+ *    [tau_min,tau_max]), Cmid[deg*(deg+1)] = basis at the mid-points (mpopt.py:350-359).
+ *    Any output pointer may be NULL. */
+int mpx_collocation_tables(int32_t scheme, int32_t deg, double tau_min, double tau_max, int32_t device,
+                           double* roots, double* D, double* w, double* Cmid);
+
+/* -- basis at arbitrary points: get_diff_matrix(key, taus, order) / get_interpolation_matrix
+ *    (mpopt.py:3815-3849, :3884-3905) and get_quadrature_weights(key, tau0, tau1) (:3851-3882).
+ *    order 0 -> C[n_taus][deg+1] = l_j(tau_i); order 1|2 -> derivatives. */
+int mpx_collocation_basis_at(int32_t scheme, int32_t deg, double tau_min, double tau_max, int32_t device,
+                             int32_t order, int32_t n_taus, const double* taus, double* out);
+int mpx_collocation_weights(int32_t scheme, int32_t deg, double tau_min, double tau_max, int32_t device,
+                            double tau0, double tau1, double* w);
+
+/* -- plan: replaces mpopt.create_nlp + create_solver's ca.nlpsol(...) function derivation
+ *    (mpopt.py:574-639, :725-758). */
+int mpx_plan_create(const mpx_problem_desc* desc, mpx_plan** out);
+void mpx_plan_destroy(mpx_plan* plan);
+
+int mpx_sizes(const mpx_plan* plan, int64_t* n_z, int64_t* n_p, int64_t* n_g, int64_t* nnz_jac);
+/* CSR pattern of jac_g: rowptr[n_g+1], colind[nnz] (sorted within each row). */
+int mpx_jac_structure(const mpx_plan* plan, int64_t* rowptr, int64_t* colind);
+/* CCS pattern (CasADi's native order) + permutation: ccs_values[i] = csr_values[perm[i]]. */
+int mpx_jac_structure_ccs(const mpx_plan* plan, int64_t* colptr, int64_t* rowind, int64_t* perm);
+/* tables the plan uses for one degree (same layout as mpx_collocation_tables) */
+int mpx_plan_tables(const mpx_plan* plan, int32_t deg, double* roots, double* D, double* w, double* Cmid);
+/* contiguous runs of g / values written by this plan's shard: pairs (offset, count).
+ * Call with runs == NULL to get the count. kind 0: g, 1: jac values, 2: grad_f. */
+int mpx_shard_runs(const mpx_plan* plan, int32_t kind, int64_t* runs, int64_t* n_runs);
+
+/* -- evaluators: replace CasADi's nlp_f / nlp_grad_f / nlp_g / nlp_jac_g (derived at
+ *    mpopt.py:757, called inside mpopt.py:804). z[n_z], p[n_p] host pointers. */
+int mpx_eval_f(mpx_plan* plan, const double* z, const double* p, double* f);
+int mpx_eval_grad_f(mpx_plan* plan, const double* z, const double* p, double* f_or_null, double* grad);
+int mpx_eval_g(mpx_plan* plan, const double* z, const double* p, double* g);
+int mpx_eval_jac_g(mpx_plan* plan, const double* z, const double* p, double* g_or_null, double* values);
+
+/* -- device-pointer variants (stream: cudaStream_t, NULL = the plan's own stream).
+ *    f_dev: 1 double; they enqueue work and return without synchronising. */
+int mpx_eval_f_grad_dev(mpx_plan* plan, const double* d_z, const double* d_p, double* d_f, double* d_grad_or_null,
+                        void* stream);
+int mpx_eval_g_jac_dev(mpx_plan* plan, const double* d_z, const double* d_p, double* d_g, double* d_values_or_null,
+                       void* stream);
+int mpx_sync(mpx_plan* plan);
+
+/* number of kernel launches issued by this plan so far (bench.py's gpu_launches) */
+int64_t mpx_launch_count(const mpx_plan* plan);
+/* human-readable description of how the node functors were obtained ("aot:<key>" / "nvrtc:<key>") */
+const char* mpx_program_origin(const mpx_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPX_H_ */

@@ -1,0 +1,921 @@
+// mpx_plan.cu -- the C ABI of include/mpx.h: plan creation (layout, CSR structure, device
+// tables), the program registry, and the evaluators that launch the kernels of
+// mpx_kernels.cuh.  Host code here is index logic only; every floating-point value of the
+// hot path is produced on the device.
+//
+// Layout being reproduced (reference: /root/reference/mpopt/mpopt.py):
+//   variables  :537-543, :627      z = per phase [X(:,0..nx-1) | U(:,0..nu-1) | t0 | tf | a]
+//   rows       :458, :617-621      per phase [F | C | DU | mU | dU | TC], then the event blocks
+//   ownership  :189-195            a shared segment-boundary node belongs to the earlier segment
+//   staircase  :4015-4039          composite D; :4066-4096 composite mid-point interpolation
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/mpx.h"
+#include "mpx_kernels.cuh"
+#include "mpx_program.h"
+#include "mpx_tables.cuh"
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t e_ = (expr);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? MPX_ENODEVICE : MPX_ECUDA, \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                                 \
+  } while (0)
+
+extern "C" int mpx_version(void) { return MPX_VERSION; }
+extern "C" const char* mpx_last_error(void) { return g_err.c_str(); }
+
+// ------------------------------------------------------------------ program registry
+static MpxProgramEntry* g_programs = nullptr;
+extern "C" void mpx_register_program(MpxProgramEntry* e) {
+  e->next = g_programs;
+  g_programs = e;
+}
+const MpxProgramEntry* mpx_find_program(const char* key) {
+  if (!key) return nullptr;
+  for (MpxProgramEntry* e = g_programs; e; e = e->next)
+    if (strcmp(e->key, key) == 0) return e;
+  return nullptr;
+}
+
+// ------------------------------------------------------------------ small generic kernels
+// slope-continuity rows (mpopt.py:379-413): row (c,k) = D_k(tau1) - D_{k+1}(tau0) applied to U(:,c)
+struct MpxDuArgs {
+  const double* z;
+  const double* tabs;
+  const int32_t* seg_tab;
+  const int32_t* seg_start;
+  const int64_t* seg_spre;
+  double* g;
+  double* vals;
+  int32_t K, N, nx, nu;
+  int64_t zoff, gdU, vdU, nnzS;
+};
+__global__ void mpx_ducont_kernel(const MpxDuArgs A, int k_begin, int k_end, int jac) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nk = k_end - k_begin;
+  if (i >= nk * A.nu) return;
+  const int c = i / nk, k = k_begin + (i - c * nk);
+  const int s0 = A.seg_start[k], s1 = A.seg_start[k + 1], s2 = A.seg_start[k + 2];
+  const int da = s1 - s0, db = s2 - s1, na1 = da + 1, nb1 = db + 1;
+  const double* Da = A.tabs + A.seg_tab[k] + MpxTab::off_D(na1) + da * na1;  // last row of D_k
+  const double* Db = A.tabs + A.seg_tab[k + 1] + MpxTab::off_D(nb1);        // first row of D_{k+1}
+  const double* U = A.z + A.zoff + (int64_t)(A.nx + c) * A.N;
+  double* v = A.vals + A.vdU + (int64_t)c * A.nnzS + A.seg_spre[k];
+  double acc = 0.0;
+  for (int j = 0; j < da; ++j) {
+    acc = fma(Da[j], U[s0 + j], acc);
+    if (jac) v[j] = Da[j];
+  }
+  const double mid = Da[da] - Db[0];
+  acc = fma(mid, U[s1], acc);
+  if (jac) v[da] = mid;
+  for (int j = 1; j <= db; ++j) {
+    acc = fma(-Db[j], U[s1 + j], acc);
+    if (jac) v[da + j] = -Db[j];
+  }
+  A.g[A.gdU + (int64_t)c * (A.K - 1) + k] = acc;
+}
+
+// phase-link rows (mpopt.py:464-521): one thread per row
+struct MpxEvArgs {
+  const double* z;
+  double* g;
+  double* vals;
+  const int64_t* col_a;  // [rows] column with coefficient +1
+  const int64_t* col_b;  // [rows] column with coefficient -1
+  int64_t g0, v0;
+  int32_t rows;
+};
+__global__ void mpx_events_kernel(const MpxEvArgs A, int jac) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= A.rows) return;
+  const int64_t ca = A.col_a[r], cb = A.col_b[r];
+  A.g[A.g0 + r] = A.z[ca] - A.z[cb];
+  if (jac) {  // sorted columns within the row
+    A.vals[A.v0 + 2 * r] = ca < cb ? 1.0 : -1.0;
+    A.vals[A.v0 + 2 * r + 1] = ca < cb ? -1.0 : 1.0;
+  }
+}
+
+// drop masked entries (exact-zero table values, SX folding -- SURVEY.md Q10)
+__global__ void mpx_compact_kernel(const double* __restrict__ full, const int64_t* __restrict__ map, double* out,
+                                   int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = full[map[i]];
+}
+
+// exclusive prefix sum of the segment widths of every phase (time grid, mpopt.py:192)
+__global__ void mpx_scan_widths_kernel(const double* w, double* sig0, int K) {
+  const double* wp = w + (int64_t)blockIdx.x * K;
+  double* sp = sig0 + (int64_t)blockIdx.x * K;
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    for (int k = 0; k < K; ++k) {
+      sp[k] = acc;
+      acc += wp[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ plan
+struct PhaseLayout {
+  int nc = 0, ntc = 0;
+  bool has_DU = false, has_mU = false, has_dU = false;
+  std::vector<int> f_next, c_len, tc_len;
+  std::vector<uint8_t> pat_f, f_nz, f_t, pat_c, c_t, pat_tc;
+  int64_t zoff = 0, n_g = 0;
+  int64_t gF = 0, gC = 0, gDU = 0, gmU = 0, gdU = 0, gTC = 0;
+  int64_t vF[MPX_MAXS], vC[MPX_MAXS];
+  int64_t vDU = 0, vmU = 0, vdU = 0, vTC = 0;
+  bool uses_t = false, cost_t = false;
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+  cudaError_t ensure(size_t n) {
+    if (n <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr, bytes = 0;
+    cudaError_t e = cudaMalloc(&p, n ? n : 8);
+    if (e == cudaSuccess) bytes = n;
+    return e;
+  }
+  template <class T>
+  T* as() const {
+    return reinterpret_cast<T*>(p);
+  }
+};
+
+struct mpx_plan {
+  int nx, nu, na, P, K, N, scheme, device;
+  double tau_min, tau_max, st;
+  std::vector<int> po, seg_start;
+  std::vector<double> sx, su, sa;
+  std::vector<int> links;
+  int seg_begin, seg_end;
+  bool drop, uniform;
+  int64_t nvar, n_z, n_p, n_g, nnz_full, nnz;
+  int64_t nnzD, nnzI, nnzS;
+  int64_t g_events, v_events;
+  std::vector<PhaseLayout> ph;
+  // unique degrees and their table records
+  std::vector<int> degs, rec_off;
+  std::vector<double> h_tabs;
+  int tab_doubles;
+  // structure (compact = what the caller sees)
+  std::vector<int64_t> rowptr, colind, gather;  // gather: compact -> full index (empty when identical)
+  // device
+  cudaStream_t stream = nullptr;
+  DevBuf d_tabs, d_seg_tab, d_seg_start, d_seg_dpre, d_seg_ipre, d_seg_spre, d_z, d_p, d_sig0, d_g, d_vals, d_full,
+      d_grad, d_partial, d_f, d_gather, d_evcols;
+  std::vector<double> h_p_cache;
+  bool p_valid = false;
+  const MpxProgramEntry* prog = nullptr;
+  std::string origin;
+  std::vector<MpxPhaseArgs> args;
+  int64_t launches = 0;
+  int smem_gjac = 0, smem_g = 0, smem_fgrad = 0;
+  ~mpx_plan() {
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+static int compute_tables(int scheme, const std::vector<int>& degs, const std::vector<int>& rec_off, int total,
+                          double tmin, double tmax, double* d_recs, cudaStream_t st) {
+  DevBuf dd, doff;
+  CUDA_TRY(dd.ensure(degs.size() * sizeof(int)));
+  CUDA_TRY(doff.ensure(degs.size() * sizeof(int)));
+  CUDA_TRY(cudaMemcpyAsync(dd.p, degs.data(), degs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(doff.p, rec_off.data(), degs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(d_recs, 0, (size_t)total * sizeof(double), st));
+  int dmax = *std::max_element(degs.begin(), degs.end());
+  size_t smem = (size_t)(2 * (dmax + 1) + 8) * sizeof(double);
+  mpx_tables_kernel<<<(int)degs.size(), MPX_TAB_THREADS, smem, st>>>(scheme, dd.as<int>(), doff.as<int>(), tmin, tmax,
+                                                                    d_recs);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return MPX_OK;
+}
+
+static int check_degree(int scheme, int deg) {
+  if (scheme < MPX_LGR || scheme > MPX_CGL) return fail(MPX_EINVAL, "unknown collocation scheme");
+  if (deg < 1 || deg > MPX_MAX_DEG) return fail(MPX_ELIMIT, "polynomial degree must be in [1, 200]");
+  return MPX_OK;
+}
+
+extern "C" int mpx_collocation_tables(int32_t scheme, int32_t deg, double tau_min, double tau_max, int32_t device,
+                                      double* roots, double* D, double* w, double* Cmid) {
+  int rc = check_degree(scheme, deg);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(device));
+  const int n1 = deg + 1, total = MpxTab::size(n1);
+  DevBuf rec;
+  CUDA_TRY(rec.ensure((size_t)total * sizeof(double)));
+  std::vector<int> degs{deg}, off{0};
+  rc = compute_tables(scheme, degs, off, total, tau_min, tau_max, rec.as<double>(), 0);
+  if (rc) return rc;
+  std::vector<double> h(total);
+  CUDA_TRY(cudaMemcpy(h.data(), rec.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost));
+  if (roots) memcpy(roots, h.data() + MpxTab::off_roots(n1), n1 * sizeof(double));
+  if (w) memcpy(w, h.data() + MpxTab::off_w(n1), n1 * sizeof(double));
+  if (D) memcpy(D, h.data() + MpxTab::off_D(n1), (size_t)n1 * n1 * sizeof(double));
+  if (Cmid) memcpy(Cmid, h.data() + MpxTab::off_C(n1), (size_t)deg * n1 * sizeof(double));
+  return MPX_OK;
+}
+
+extern "C" int mpx_collocation_basis_at(int32_t scheme, int32_t deg, double tau_min, double tau_max, int32_t device,
+                                        int32_t order, int32_t n_taus, const double* taus, double* out) {
+  int rc = check_degree(scheme, deg);
+  if (rc) return rc;
+  if (order < 0 || order > 2 || n_taus < 0 || (n_taus && (!taus || !out))) return fail(MPX_EINVAL, "bad basis_at arguments");
+  if (n_taus == 0) return MPX_OK;
+  CUDA_TRY(cudaSetDevice(device));
+  const int n1 = deg + 1;
+  DevBuf dt, dout;
+  CUDA_TRY(dt.ensure((size_t)n_taus * sizeof(double)));
+  CUDA_TRY(dout.ensure((size_t)n_taus * n1 * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(dt.p, taus, (size_t)n_taus * sizeof(double), cudaMemcpyHostToDevice));
+  mpx_basis_at_kernel<<<1, MPX_TAB_THREADS, (size_t)(n1 + 2) * sizeof(double)>>>(scheme, deg, tau_min, tau_max, order,
+                                                                                n_taus, dt.as<double>(), dout.as<double>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(out, dout.p, (size_t)n_taus * n1 * sizeof(double), cudaMemcpyDeviceToHost));
+  return MPX_OK;
+}
+
+extern "C" int mpx_collocation_weights(int32_t scheme, int32_t deg, double tau_min, double tau_max, int32_t device,
+                                       double tau0, double tau1, double* w) {
+  int rc = check_degree(scheme, deg);
+  if (rc) return rc;
+  if (!w) return fail(MPX_EINVAL, "w is NULL");
+  CUDA_TRY(cudaSetDevice(device));
+  const int n1 = deg + 1;
+  DevBuf dw;
+  CUDA_TRY(dw.ensure((size_t)n1 * sizeof(double)));
+  mpx_weights_kernel<<<1, MPX_TAB_THREADS, (size_t)(2 * n1 + 8) * sizeof(double)>>>(scheme, deg, tau_min, tau_max, tau0,
+                                                                                   tau1, dw.as<double>());
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpy(w, dw.p, (size_t)n1 * sizeof(double), cudaMemcpyDeviceToHost));
+  return MPX_OK;
+}
+
+// ------------------------------------------------------------------ structure
+namespace {
+struct Builder {
+  mpx_plan& P;
+  std::vector<int64_t> rowptr, colind;
+  std::vector<uint8_t> keep;
+  explicit Builder(mpx_plan& p) : P(p) { rowptr.push_back(0); }
+  void add(int64_t col, bool k = true) {
+    colind.push_back(col);
+    keep.push_back(k ? 1 : 0);
+  }
+  void end_row() { rowptr.push_back((int64_t)colind.size()); }
+};
+}  // namespace
+
+static const double* tab_of(const mpx_plan& p, int deg) {
+  for (size_t i = 0; i < p.degs.size(); ++i)
+    if (p.degs[i] == deg) return p.h_tabs.data() + p.rec_off[i];
+  return nullptr;
+}
+
+static void build_structure(mpx_plan& p) {
+  Builder B(p);
+  const int nx = p.nx, nu = p.nu, na = p.na, N = p.N, K = p.K;
+  const int nv = nx + nu + na;
+  // node -> (owner segment, local index)
+  std::vector<int> nseg(N), nloc(N);
+  for (int k = 0; k < K; ++k)
+    for (int r = (k == 0 ? 0 : 1); r <= p.po[k]; ++r) nseg[p.seg_start[k] + r] = k, nloc[p.seg_start[k] + r] = r;
+  for (int ph = 0; ph < p.P; ++ph) {
+    const PhaseLayout& L = p.ph[ph];
+    const int64_t zo = L.zoff;
+    auto colX = [&](int i, int s) { return zo + (int64_t)s * N + i; };
+    auto colU = [&](int i, int c) { return zo + (int64_t)(nx + c) * N + i; };
+    const int64_t cT0 = zo + (int64_t)(nx + nu) * N, cTF = cT0 + 1;
+    auto colA = [&](int m) { return cT0 + 2 + m; };
+    // F rows
+    for (int s = 0; s < nx; ++s) {
+      const uint8_t* pat = L.pat_f.data() + (size_t)s * nv;
+      for (int i = 0; i < N; ++i) {
+        const int k = nseg[i], r = nloc[i], d = p.po[k], n1 = d + 1;
+        const double* D = tab_of(p, d) + MpxTab::off_D(n1);
+        for (int sp = 0; sp < s; ++sp)
+          if (pat[sp]) B.add(colX(i, sp));
+        for (int j = 0; j <= d; ++j) {
+          bool keep = true;
+          if (p.drop && D[r * n1 + j] == 0.0 && !(j == r && pat[s])) keep = false;
+          B.add(colX(p.seg_start[k] + j, s), keep);
+        }
+        for (int sp = s + 1; sp < nx; ++sp)
+          if (pat[sp]) B.add(colX(i, sp));
+        for (int c = 0; c < nu; ++c)
+          if (pat[nx + c]) B.add(colU(i, c));
+        if (L.f_nz[s]) B.add(cT0), B.add(cTF);
+        for (int m = 0; m < na; ++m)
+          if (pat[nx + nu + m]) B.add(colA(m));
+        B.end_row();
+      }
+    }
+    // path rows
+    for (int q = 0; q < L.nc; ++q) {
+      const uint8_t* pat = L.pat_c.data() + (size_t)q * nv;
+      for (int i = 0; i < N; ++i) {
+        for (int s = 0; s < nx; ++s)
+          if (pat[s]) B.add(colX(i, s));
+        for (int c = 0; c < nu; ++c)
+          if (pat[nx + c]) B.add(colU(i, c));
+        if (L.c_t[q]) B.add(cT0), B.add(cTF, i != 0);  // node 0: t = t0 + h*0.0 folds to t0 (mpopt.py:198)
+        for (int m = 0; m < na; ++m)
+          if (pat[nx + nu + m]) B.add(colA(m));
+        B.end_row();
+      }
+    }
+    // control slope rows
+    if (L.has_DU)
+      for (int c = 0; c < nu; ++c)
+        for (int i = 0; i < N; ++i) {
+          const int k = nseg[i], r = nloc[i], d = p.po[k], n1 = d + 1;
+          const double* D = tab_of(p, d) + MpxTab::off_D(n1);
+          for (int j = 0; j <= d; ++j) B.add(colU(p.seg_start[k] + j, c), !(p.drop && D[r * n1 + j] == 0.0));
+          B.end_row();
+        }
+    // mid-point rows
+    if (L.has_mU)
+      for (int c = 0; c < nu; ++c)
+        for (int k = 0; k < K; ++k) {
+          const int d = p.po[k], n1 = d + 1;
+          const double* C = tab_of(p, d) + MpxTab::off_C(n1);
+          for (int m = 0; m < d; ++m) {
+            for (int j = 0; j <= d; ++j) B.add(colU(p.seg_start[k] + j, c), !(p.drop && C[m * n1 + j] == 0.0));
+            B.end_row();
+          }
+        }
+    // slope continuity rows
+    if (L.has_dU)
+      for (int c = 0; c < nu; ++c)
+        for (int k = 0; k + 1 < K; ++k) {
+          const int da = p.po[k], db = p.po[k + 1], na1 = da + 1, nb1 = db + 1;
+          const double* Da = tab_of(p, da) + MpxTab::off_D(na1) + da * na1;
+          const double* Db = tab_of(p, db) + MpxTab::off_D(nb1);
+          for (int j = 0; j < da; ++j) B.add(colU(p.seg_start[k] + j, c), !(p.drop && Da[j] == 0.0));
+          B.add(colU(p.seg_start[k + 1], c), !(p.drop && Da[da] - Db[0] == 0.0));
+          for (int j = 1; j <= db; ++j) B.add(colU(p.seg_start[k + 1] + j, c), !(p.drop && Db[j] == 0.0));
+          B.end_row();
+        }
+    // terminal rows: x0_s (col s*N) then xf_s (col s*N+N-1) per state, T0, TF, a
+    const int ntv = 2 * nx + 2 + na;
+    for (int r = 0; r < L.ntc; ++r) {
+      const uint8_t* pat = L.pat_tc.data() + (size_t)r * ntv;
+      for (int s = 0; s < nx; ++s) {
+        if (pat[nx + s]) B.add(colX(0, s));
+        if (pat[s]) B.add(colX(N - 1, s));
+      }
+      if (pat[2 * nx + 1]) B.add(cT0);
+      if (pat[2 * nx]) B.add(cTF);
+      for (int m = 0; m < na; ++m)
+        if (pat[2 * nx + 2 + m]) B.add(colA(m));
+      B.end_row();
+    }
+  }
+  // event rows: state block, control block, time block (mpopt.py:484-519)
+  const int nl = (int)p.links.size() / 2;
+  std::vector<int64_t> ca, cb;
+  auto ev = [&](int64_t a, int64_t b) {
+    ca.push_back(a), cb.push_back(b);
+    B.add(std::min(a, b)), B.add(std::max(a, b));
+    B.end_row();
+  };
+  for (int l = 0; l < nl; ++l)
+    for (int s = 0; s < nx; ++s)
+      ev(p.ph[p.links[2 * l + 1]].zoff + (int64_t)s * N, p.ph[p.links[2 * l]].zoff + (int64_t)s * N + N - 1);
+  for (int l = 0; l < nl; ++l)
+    for (int c = 0; c < nu; ++c)
+      ev(p.ph[p.links[2 * l + 1]].zoff + (int64_t)(nx + c) * N, p.ph[p.links[2 * l]].zoff + (int64_t)(nx + c) * N + N - 1);
+  for (int l = 0; l < nl; ++l)
+    ev(p.ph[p.links[2 * l + 1]].zoff + (int64_t)(nx + nu) * N, p.ph[p.links[2 * l]].zoff + (int64_t)(nx + nu) * N + 1);
+  // event columns for the device kernel
+  if (nl) {
+    std::vector<int64_t> both(ca);
+    both.insert(both.end(), cb.begin(), cb.end());
+    p.d_evcols.ensure(both.size() * sizeof(int64_t));
+    cudaMemcpy(p.d_evcols.p, both.data(), both.size() * sizeof(int64_t), cudaMemcpyHostToDevice);
+  }
+  // compact
+  p.nnz_full = (int64_t)B.colind.size();
+  bool all = true;
+  for (uint8_t k : B.keep)
+    if (!k) {
+      all = false;
+      break;
+    }
+  if (all) {
+    p.rowptr.swap(B.rowptr);
+    p.colind.swap(B.colind);
+    p.gather.clear();
+  } else {
+    p.rowptr.assign(1, 0);
+    p.colind.clear();
+    p.gather.clear();
+    for (size_t r = 0; r + 1 < B.rowptr.size(); ++r) {
+      for (int64_t e = B.rowptr[r]; e < B.rowptr[r + 1]; ++e)
+        if (B.keep[e]) p.colind.push_back(B.colind[e]), p.gather.push_back(e);
+      p.rowptr.push_back((int64_t)p.colind.size());
+    }
+  }
+  p.nnz = (int64_t)p.colind.size();
+}
+
+// ------------------------------------------------------------------ plan creation
+static void copy_pat(std::vector<uint8_t>& dst, const uint8_t* src, size_t n) {
+  dst.assign(n, 0);
+  if (src)
+    for (size_t i = 0; i < n; ++i) dst[i] = src[i] ? 1 : 0;
+}
+
+extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
+  if (!d || !out) return fail(MPX_EINVAL, "NULL argument");
+  *out = nullptr;
+  if (d->nx < 0 || d->nu < 0 || d->na < 0 || d->nx > MPX_MAXS || d->nu > MPX_MAXS || d->na > MPX_MAXS)
+    return fail(MPX_ELIMIT, "nx, nu, na must be in [0, 16]");
+  if (d->n_phases < 1 || !d->phases) return fail(MPX_EINVAL, "n_phases must be >= 1");
+  if (d->n_segments < 1 || !d->poly_orders) return fail(MPX_EINVAL, "n_segments must be >= 1");
+  if (d->scheme < MPX_LGR || d->scheme > MPX_CGL) return fail(MPX_EINVAL, "unknown collocation scheme");
+  if (!(d->tau_max > d->tau_min)) return fail(MPX_EINVAL, "tau_max must exceed tau_min");
+  for (int k = 0; k < d->n_segments; ++k)
+    if (d->poly_orders[k] < 1 || d->poly_orders[k] > MPX_MAX_DEG)
+      return fail(MPX_ELIMIT, "every poly_order must be in [1, 200]");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0 || d->device < 0 || d->device >= ndev) return fail(MPX_ENODEVICE, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(d->device));
+
+  std::unique_ptr<mpx_plan> pp(new mpx_plan());
+  mpx_plan& p = *pp;
+  p.nx = d->nx, p.nu = d->nu, p.na = d->na, p.P = d->n_phases, p.K = d->n_segments, p.scheme = d->scheme;
+  p.device = d->device, p.tau_min = d->tau_min, p.tau_max = d->tau_max, p.st = d->scale_t;
+  p.drop = d->drop_exact_zeros != 0;
+  p.po.assign(d->poly_orders, d->poly_orders + p.K);
+  p.seg_start.assign(p.K + 1, 0);
+  for (int k = 0; k < p.K; ++k) p.seg_start[k + 1] = p.seg_start[k] + p.po[k];
+  p.N = p.seg_start[p.K] + 1;
+  p.uniform = std::all_of(p.po.begin(), p.po.end(), [&](int v) { return v == p.po[0]; });
+  p.sx.assign(p.nx, 1.0), p.su.assign(p.nu, 1.0), p.sa.assign(p.na, 1.0);
+  for (int i = 0; i < p.nx && d->scale_x; ++i) p.sx[i] = d->scale_x[i];
+  for (int i = 0; i < p.nu && d->scale_u; ++i) p.su[i] = d->scale_u[i];
+  for (int i = 0; i < p.na && d->scale_a; ++i) p.sa[i] = d->scale_a[i];
+  if (p.st == 0.0) return fail(MPX_EINVAL, "scale_t must be non-zero");
+  p.seg_begin = d->seg_begin, p.seg_end = d->seg_end;
+  if (p.seg_begin == 0 && p.seg_end == 0) p.seg_end = p.K;
+  if (p.seg_begin < 0 || p.seg_end > p.K || p.seg_begin >= p.seg_end) return fail(MPX_EINVAL, "bad segment shard");
+  if (d->n_links < 0 || (d->n_links && !d->links)) return fail(MPX_EINVAL, "bad phase links");
+  p.links.assign(d->links, d->links + 2 * d->n_links);
+  for (int v : p.links)
+    if (v < 0 || v >= p.P) return fail(MPX_EINVAL, "phase link out of range");
+
+  // ---- program
+  p.prog = mpx_find_program(d->program_key);
+  if (!p.prog)
+    return fail(MPX_ENOPROGRAM, std::string("no compiled node functors registered for program key '") +
+                                    (d->program_key ? d->program_key : "(null)") + "'");
+  if (p.prog->n_phases != p.P) return fail(MPX_EINVAL, "program/phase count mismatch");
+  p.origin = std::string("aot:") + p.prog->key;
+
+  // ---- sizes and offsets
+  const int nx = p.nx, nu = p.nu, na = p.na, N = p.N, K = p.K, nv = nx + nu + na;
+  p.nvar = (int64_t)N * (nx + nu) + 2 + na;
+  p.n_z = p.nvar * p.P;
+  p.n_p = (int64_t)K * p.P;
+  p.nnzD = (int64_t)(p.po[0] + 1) * (p.po[0] + 1);
+  p.nnzI = 0, p.nnzS = 0;
+  for (int k = 0; k < K; ++k) {
+    if (k) p.nnzD += (int64_t)p.po[k] * (p.po[k] + 1);
+    p.nnzI += (int64_t)p.po[k] * (p.po[k] + 1);
+    if (k + 1 < K) p.nnzS += p.po[k] + p.po[k + 1] + 1;
+  }
+  p.ph.resize(p.P);
+  int64_t row = 0, val = 0;
+  for (int ph = 0; ph < p.P; ++ph) {
+    const mpx_phase_desc& q = d->phases[ph];
+    PhaseLayout& L = p.ph[ph];
+    if (q.n_path < 0 || q.n_path > MPX_MAXS || q.n_term < 0) return fail(MPX_ELIMIT, "n_path must be in [0,16]");
+    L.nc = q.n_path, L.ntc = q.n_term;
+    copy_pat(L.pat_f, q.pat_f, (size_t)nx * nv);
+    copy_pat(L.f_nz, q.f_nz, nx);
+    copy_pat(L.f_t, q.f_t, nx);
+    copy_pat(L.pat_c, q.pat_c, (size_t)L.nc * nv);
+    copy_pat(L.c_t, q.c_t, L.nc);
+    copy_pat(L.pat_tc, q.pat_tc, (size_t)L.ntc * (2 * nx + 2 + na));
+    L.has_DU = q.diff_u != 0, L.has_mU = q.midu != 0, L.has_dU = q.du_continuity != 0 && K > 1;
+    L.zoff = p.nvar * ph;
+    L.cost_t = q.cost_t != 0;
+    L.f_next.assign(nx, 0), L.c_len.assign(L.nc, 0), L.tc_len.assign(L.ntc, 0);
+    for (int s = 0; s < nx; ++s) {
+      int n = 2 * L.f_nz[s];
+      for (int v = 0; v < nv; ++v)
+        if (v != s && L.pat_f[(size_t)s * nv + v]) ++n;
+      L.f_next[s] = n;
+      L.uses_t |= L.f_t[s] != 0;
+    }
+    for (int c = 0; c < L.nc; ++c) {
+      int n = 2 * L.c_t[c];
+      for (int v = 0; v < nv; ++v) n += L.pat_c[(size_t)c * nv + v];
+      L.c_len[c] = n;
+      L.uses_t |= L.c_t[c] != 0;
+    }
+    for (int r = 0; r < L.ntc; ++r)
+      for (int v = 0; v < 2 * nx + 2 + na; ++v) L.tc_len[r] += L.pat_tc[(size_t)r * (2 * nx + 2 + na) + v];
+    L.gF = row, row += (int64_t)nx * N;
+    L.gC = row, row += (int64_t)L.nc * N;
+    L.gDU = row, row += L.has_DU ? (int64_t)nu * N : 0;
+    L.gmU = row, row += L.has_mU ? (int64_t)nu * (N - 1) : 0;
+    L.gdU = row, row += L.has_dU ? (int64_t)nu * (K - 1) : 0;
+    L.gTC = row, row += L.ntc;
+    for (int s = 0; s < nx; ++s) L.vF[s] = val, val += p.nnzD + (int64_t)N * L.f_next[s];
+    for (int c = 0; c < L.nc; ++c) L.vC[c] = val, val += (int64_t)N * L.c_len[c];
+    L.vDU = val, val += L.has_DU ? (int64_t)nu * p.nnzD : 0;
+    L.vmU = val, val += L.has_mU ? (int64_t)nu * p.nnzI : 0;
+    L.vdU = val, val += L.has_dU ? (int64_t)nu * p.nnzS : 0;
+    L.vTC = val;
+    for (int r = 0; r < L.ntc; ++r) val += L.tc_len[r];
+  }
+  p.g_events = row, p.v_events = val;
+  const int nl = d->n_links;
+  p.n_g = row + (int64_t)nl * (nx + nu + 1);
+
+  // ---- tables on the device (K0/K1), copied back once for the exact-zero mask
+  CUDA_TRY(cudaStreamCreateWithFlags(&p.stream, cudaStreamNonBlocking));
+  p.degs = p.po;
+  std::sort(p.degs.begin(), p.degs.end());
+  p.degs.erase(std::unique(p.degs.begin(), p.degs.end()), p.degs.end());
+  p.rec_off.clear();
+  int total = 0;
+  for (int dg : p.degs) p.rec_off.push_back(total), total += MpxTab::size(dg + 1);
+  p.tab_doubles = total;
+  CUDA_TRY(p.d_tabs.ensure((size_t)total * sizeof(double)));
+  int rc = compute_tables(p.scheme, p.degs, p.rec_off, total, p.tau_min, p.tau_max, p.d_tabs.as<double>(), p.stream);
+  if (rc) return rc;
+  p.h_tabs.resize(total);
+  CUDA_TRY(cudaMemcpy(p.h_tabs.data(), p.d_tabs.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost));
+
+  // ---- per-segment index tables
+  std::vector<int32_t> seg_tab(K);
+  std::vector<int64_t> dpre(K), ipre(K), spre(K);
+  int64_t accD = 0, accI = 0, accS = 0;
+  int dmax = 0;
+  for (int k = 0; k < K; ++k) {
+    const int dg = p.po[k];
+    dmax = std::max(dmax, dg);
+    seg_tab[k] = p.rec_off[std::lower_bound(p.degs.begin(), p.degs.end(), dg) - p.degs.begin()];
+    dpre[k] = accD, ipre[k] = accI, spre[k] = accS;
+    accD += k == 0 ? (int64_t)(dg + 1) * (dg + 1) : (int64_t)dg * (dg + 1);
+    accI += (int64_t)dg * (dg + 1);
+    if (k + 1 < K) accS += dg + p.po[k + 1] + 1;
+  }
+  auto up = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = b.ensure(bytes);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+  };
+  CUDA_TRY(up(p.d_seg_tab, seg_tab.data(), K * sizeof(int32_t)));
+  CUDA_TRY(up(p.d_seg_start, p.seg_start.data(), (K + 1) * sizeof(int32_t)));
+  CUDA_TRY(up(p.d_seg_dpre, dpre.data(), K * sizeof(int64_t)));
+  CUDA_TRY(up(p.d_seg_ipre, ipre.data(), K * sizeof(int64_t)));
+  CUDA_TRY(up(p.d_seg_spre, spre.data(), K * sizeof(int64_t)));
+
+  build_structure(p);
+  if (!p.gather.empty()) CUDA_TRY(up(p.d_gather, p.gather.data(), p.gather.size() * sizeof(int64_t)));
+
+  // ---- work buffers
+  CUDA_TRY(p.d_z.ensure((size_t)p.n_z * sizeof(double)));
+  CUDA_TRY(p.d_p.ensure((size_t)p.n_p * sizeof(double)));
+  CUDA_TRY(p.d_sig0.ensure((size_t)p.n_p * sizeof(double)));
+  CUDA_TRY(p.d_g.ensure((size_t)p.n_g * sizeof(double)));
+  CUDA_TRY(p.d_vals.ensure((size_t)p.nnz * sizeof(double)));
+  if (!p.gather.empty()) CUDA_TRY(p.d_full.ensure((size_t)p.nnz_full * sizeof(double)));
+  CUDA_TRY(p.d_grad.ensure((size_t)p.n_z * sizeof(double)));
+  CUDA_TRY(p.d_partial.ensure((size_t)p.n_p * MPX_NPART * sizeof(double)));
+  CUDA_TRY(p.d_f.ensure(sizeof(double)));
+
+  // ---- shared-memory budget (same formulas as the kernels)
+  {
+    const int n1 = dmax + 1;
+    int base = MpxTab::size(n1) + MpxTab::pad2((nx + nu) * n1) + 2 * MpxTab::pad2(nx * n1) + 2;
+    int stage = 0;
+    for (int ph = 0; ph < p.P; ++ph) {
+      int s_ = 0;
+      for (int s = 0; s < nx; ++s) s_ += n1 * (n1 + p.ph[ph].f_next[s]);
+      for (int c = 0; c < p.ph[ph].nc; ++c) s_ += n1 * p.ph[ph].c_len[c];
+      stage = std::max(stage, s_);
+    }
+    p.smem_g = base * 8;
+    p.smem_gjac = (base + MpxTab::pad2(stage)) * 8;
+    p.smem_fgrad = (MpxTab::size(n1) + MpxTab::pad2((nx + nu) * n1) + 4 * MPX_NPART + 2) * 8;
+    if (p.smem_gjac > 227 * 1024)
+      return fail(MPX_ELIMIT, "segment too large for the shared-memory staged kernel (degree x states)");
+  }
+
+  // ---- kernel arguments per phase (pointers filled per call)
+  p.args.resize(p.P);
+  for (int ph = 0; ph < p.P; ++ph) {
+    MpxPhaseArgs& a = p.args[ph];
+    const PhaseLayout& L = p.ph[ph];
+    memset(&a, 0, sizeof(a));
+    a.tabs = p.d_tabs.as<double>();
+    a.seg_tab = p.d_seg_tab.as<int32_t>();
+    a.seg_start = p.d_seg_start.as<int32_t>();
+    a.seg_dpre = p.d_seg_dpre.as<int64_t>();
+    a.seg_ipre = p.d_seg_ipre.as<int64_t>();
+    a.K = K, a.N = N, a.seg_begin = p.seg_begin, a.seg_end = p.seg_end;
+    a.uniform_deg = p.uniform ? p.po[0] : 0;
+    a.flags = (L.has_DU ? MPX_F_DU : 0) | (L.has_mU ? MPX_F_MU : 0) | (p.seg_end == K ? MPX_F_TAIL : 0);
+    a.accumulate_f = ph > 0;
+    a.zoff = L.zoff;
+    a.gF = L.gF, a.gC = L.gC, a.gDU = L.gDU, a.gmU = L.gmU, a.gTC = L.gTC;
+    for (int s = 0; s < nx; ++s) a.vF[s] = L.vF[s];
+    for (int c = 0; c < L.nc; ++c) a.vC[c] = L.vC[c];
+    a.vDU = L.vDU, a.vmU = L.vmU, a.vTC = L.vTC;
+    a.nnzD = p.nnzD, a.nnzI = p.nnzI;
+    for (int s = 0; s < nx; ++s) a.sx[s] = p.sx[s], a.isx[s] = 1.0 / p.sx[s];
+    for (int c = 0; c < nu; ++c) a.isu[c] = 1.0 / p.su[c];
+    for (int m = 0; m < na; ++m) a.isa[m] = 1.0 / p.sa[m];
+    a.st = p.st, a.delta = p.tau_max - p.tau_min, a.tau0 = p.tau_min;
+  }
+  *out = pp.release();
+  return MPX_OK;
+}
+
+extern "C" void mpx_plan_destroy(mpx_plan* plan) {
+  if (!plan) return;
+  cudaSetDevice(plan->device);
+  delete plan;
+}
+
+extern "C" int mpx_sizes(const mpx_plan* p, int64_t* n_z, int64_t* n_p, int64_t* n_g, int64_t* nnz) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  if (n_z) *n_z = p->n_z;
+  if (n_p) *n_p = p->n_p;
+  if (n_g) *n_g = p->n_g;
+  if (nnz) *nnz = p->nnz;
+  return MPX_OK;
+}
+
+extern "C" int mpx_jac_structure(const mpx_plan* p, int64_t* rowptr, int64_t* colind) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  if (rowptr) memcpy(rowptr, p->rowptr.data(), p->rowptr.size() * sizeof(int64_t));
+  if (colind) memcpy(colind, p->colind.data(), p->colind.size() * sizeof(int64_t));
+  return MPX_OK;
+}
+
+extern "C" int mpx_jac_structure_ccs(const mpx_plan* p, int64_t* colptr, int64_t* rowind, int64_t* perm) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  std::vector<int64_t> cnt(p->n_z + 1, 0);
+  for (int64_t c : p->colind) ++cnt[c + 1];
+  for (int64_t c = 0; c < p->n_z; ++c) cnt[c + 1] += cnt[c];
+  if (colptr) memcpy(colptr, cnt.data(), (p->n_z + 1) * sizeof(int64_t));
+  std::vector<int64_t> next(cnt.begin(), cnt.end() - 1);
+  for (int64_t r = 0; r < p->n_g; ++r)
+    for (int64_t e = p->rowptr[r]; e < p->rowptr[r + 1]; ++e) {
+      const int64_t dst = next[p->colind[e]]++;
+      if (rowind) rowind[dst] = r;
+      if (perm) perm[dst] = e;
+    }
+  return MPX_OK;
+}
+
+extern "C" int mpx_plan_tables(const mpx_plan* p, int32_t deg, double* roots, double* D, double* w, double* Cmid) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  const double* h = tab_of(*p, deg);
+  if (!h) return fail(MPX_EINVAL, "degree not used by this plan");
+  const int n1 = deg + 1;
+  if (roots) memcpy(roots, h + MpxTab::off_roots(n1), n1 * sizeof(double));
+  if (w) memcpy(w, h + MpxTab::off_w(n1), n1 * sizeof(double));
+  if (D) memcpy(D, h + MpxTab::off_D(n1), (size_t)n1 * n1 * sizeof(double));
+  if (Cmid) memcpy(Cmid, h + MpxTab::off_C(n1), (size_t)deg * n1 * sizeof(double));
+  return MPX_OK;
+}
+
+// ------------------------------------------------------------------ shard runs
+extern "C" int mpx_shard_runs(const mpx_plan* p, int32_t kind, int64_t* runs, int64_t* n_runs) {
+  if (!p || !n_runs) return fail(MPX_EINVAL, "NULL argument");
+  if (!p->gather.empty() && kind == 1) return fail(MPX_EINVAL, "shard runs need an unmasked Jacobian pattern");
+  std::vector<int64_t> r;
+  const int kb = p->seg_begin, ke = p->seg_end, N = p->N, K = p->K, nx = p->nx, nu = p->nu;
+  const int64_t node_b = kb == 0 ? 0 : p->seg_start[kb] + 1, node_e = p->seg_start[ke] + 1;  // owned nodes [b, e)
+  const int64_t mid_b = p->seg_start[kb], mid_e = p->seg_start[ke];
+  int64_t dpre_b = 0, dpre_e = 0, ipre_b = 0, ipre_e = 0, spre_b = 0, spre_e = 0;
+  for (int k = 0; k < ke; ++k) {
+    const int64_t dd = k == 0 ? (int64_t)(p->po[k] + 1) * (p->po[k] + 1) : (int64_t)p->po[k] * (p->po[k] + 1);
+    const int64_t ii = (int64_t)p->po[k] * (p->po[k] + 1);
+    const int64_t ss = k + 1 < K ? p->po[k] + p->po[k + 1] + 1 : 0;
+    if (k < kb) dpre_b += dd, ipre_b += ii, spre_b += ss;
+    dpre_e += dd, ipre_e += ii, spre_e += ss;
+  }
+  const int kdu_b = kb, kdu_e = std::min(ke, K - 1);
+  const bool tail = ke == K;
+  auto push = [&](int64_t off, int64_t cnt) {
+    if (cnt > 0) r.push_back(off), r.push_back(cnt);
+  };
+  for (int ph = 0; ph < p->P; ++ph) {
+    const PhaseLayout& L = p->ph[ph];
+    if (kind == 0) {
+      for (int s = 0; s < nx; ++s) push(L.gF + (int64_t)s * N + node_b, node_e - node_b);
+      for (int c = 0; c < L.nc; ++c) push(L.gC + (int64_t)c * N + node_b, node_e - node_b);
+      if (L.has_DU)
+        for (int c = 0; c < nu; ++c) push(L.gDU + (int64_t)c * N + node_b, node_e - node_b);
+      if (L.has_mU)
+        for (int c = 0; c < nu; ++c) push(L.gmU + (int64_t)c * (N - 1) + mid_b, mid_e - mid_b);
+      if (L.has_dU)
+        for (int c = 0; c < nu; ++c) push(L.gdU + (int64_t)c * (K - 1) + kdu_b, kdu_e - kdu_b);
+      if (tail) push(L.gTC, L.ntc);
+    } else if (kind == 1) {
+      for (int s = 0; s < nx; ++s)
+        push(L.vF[s] + node_b * L.f_next[s] + dpre_b, (node_e - node_b) * L.f_next[s] + dpre_e - dpre_b);
+      for (int c = 0; c < L.nc; ++c) push(L.vC[c] + node_b * L.c_len[c], (node_e - node_b) * L.c_len[c]);
+      if (L.has_DU)
+        for (int c = 0; c < nu; ++c) push(L.vDU + (int64_t)c * p->nnzD + dpre_b, dpre_e - dpre_b);
+      if (L.has_mU)
+        for (int c = 0; c < nu; ++c) push(L.vmU + (int64_t)c * p->nnzI + ipre_b, ipre_e - ipre_b);
+      if (L.has_dU)
+        for (int c = 0; c < nu; ++c) push(L.vdU + (int64_t)c * p->nnzS + spre_b, spre_e - spre_b);
+      if (tail) {
+        int64_t n = 0;
+        for (int v : L.tc_len) n += v;
+        push(L.vTC, n);
+      }
+    } else {
+      for (int v = 0; v < nx + nu; ++v) push(L.zoff + (int64_t)v * N + node_b, node_e - node_b);
+    }
+  }
+  if (tail && kind == 0) push(p->g_events, p->n_g - p->g_events);
+  if (tail && kind == 1) push(p->v_events, p->nnz_full - p->v_events);
+  if (runs) memcpy(runs, r.data(), r.size() * sizeof(int64_t));
+  *n_runs = (int64_t)r.size() / 2;
+  return MPX_OK;
+}
+
+// ------------------------------------------------------------------ evaluation
+static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, double* d_g, double* d_vals, cudaStream_t st) {
+  const bool jac = d_vals != nullptr;
+  double* target = jac ? (p.gather.empty() ? d_vals : p.d_full.as<double>()) : nullptr;
+  const int grid = p.seg_end - p.seg_begin;
+  bool need_sig = false;
+  for (auto& L : p.ph) need_sig |= L.uses_t;
+  if (need_sig) {
+    mpx_scan_widths_kernel<<<p.P, 32, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
+    ++p.launches;
+  }
+  for (int ph = 0; ph < p.P; ++ph) {
+    MpxPhaseArgs& a = p.args[ph];
+    a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
+    a.g = d_g, a.vals = target;
+    CUDA_TRY(p.prog->phases[ph]->gjac(a, jac, grid, jac ? p.smem_gjac : p.smem_g, st));
+    ++p.launches;
+    const PhaseLayout& L = p.ph[ph];
+    if (L.has_dU) {
+      const int kb = p.seg_begin, ke = std::min(p.seg_end, p.K - 1);
+      if (ke > kb) {
+        MpxDuArgs du{d_z, p.d_tabs.as<double>(), p.d_seg_tab.as<int32_t>(), p.d_seg_start.as<int32_t>(),
+                     p.d_seg_spre.as<int64_t>(), d_g, target, p.K, p.N, p.nx, p.nu, L.zoff, L.gdU, L.vdU, p.nnzS};
+        const int n = (ke - kb) * p.nu;
+        mpx_ducont_kernel<<<(n + 127) / 128, 128, 0, st>>>(du, kb, ke, jac ? 1 : 0);
+        CUDA_TRY(cudaGetLastError());
+        ++p.launches;
+      }
+    }
+  }
+  const int nl = (int)p.links.size() / 2;
+  if (nl && p.seg_end == p.K) {
+    const int rows = nl * (p.nx + p.nu + 1);
+    MpxEvArgs ev{d_z, d_g, target, p.d_evcols.as<int64_t>(), p.d_evcols.as<int64_t>() + rows, p.g_events, p.v_events, rows};
+    mpx_events_kernel<<<(rows + 127) / 128, 128, 0, st>>>(ev, jac ? 1 : 0);
+    CUDA_TRY(cudaGetLastError());
+    ++p.launches;
+  }
+  if (jac && !p.gather.empty()) {
+    mpx_compact_kernel<<<(unsigned)((p.nnz + 255) / 256), 256, 0, st>>>(p.d_full.as<double>(), p.d_gather.as<int64_t>(),
+                                                                       d_vals, p.nnz);
+    CUDA_TRY(cudaGetLastError());
+    ++p.launches;
+  }
+  return MPX_OK;
+}
+
+static int launch_f_grad(mpx_plan& p, const double* d_z, const double* d_p, double* d_f, double* d_grad, cudaStream_t st) {
+  const bool grad = d_grad != nullptr;
+  const int grid = p.seg_end - p.seg_begin;
+  bool need_sig = false;
+  for (auto& L : p.ph) need_sig |= L.cost_t;
+  if (need_sig) {
+    mpx_scan_widths_kernel<<<p.P, 32, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
+    ++p.launches;
+  }
+  for (int ph = 0; ph < p.P; ++ph) {
+    MpxPhaseArgs& a = p.args[ph];
+    a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
+    a.grad = d_grad, a.partial = p.d_partial.as<double>() + (int64_t)ph * p.K * MPX_NPART, a.fout = d_f;
+    CUDA_TRY(p.prog->phases[ph]->fgrad(a, grad, grid, p.smem_fgrad, st));
+    CUDA_TRY(p.prog->phases[ph]->fgrad_final(a, grad, st));
+    p.launches += 2;
+  }
+  return MPX_OK;
+}
+
+static int upload_inputs(mpx_plan& p, const double* z, const double* pw) {
+  if (!z || !pw) return fail(MPX_EINVAL, "z and p must not be NULL");
+  CUDA_TRY(cudaSetDevice(p.device));
+  CUDA_TRY(cudaMemcpyAsync(p.d_z.p, z, (size_t)p.n_z * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+  if (!p.p_valid || memcmp(p.h_p_cache.data(), pw, (size_t)p.n_p * sizeof(double)) != 0) {
+    p.h_p_cache.assign(pw, pw + p.n_p);
+    CUDA_TRY(cudaMemcpyAsync(p.d_p.p, p.h_p_cache.data(), (size_t)p.n_p * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+    p.p_valid = true;
+  }
+  return MPX_OK;
+}
+
+extern "C" int mpx_eval_g(mpx_plan* p, const double* z, const double* pw, double* g) {
+  if (!p || !g) return fail(MPX_EINVAL, "NULL argument");
+  int rc = upload_inputs(*p, z, pw);
+  if (rc) return rc;
+  rc = launch_g_jac(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_g.as<double>(), nullptr, p->stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g, p->d_g.p, (size_t)p->n_g * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+extern "C" int mpx_eval_jac_g(mpx_plan* p, const double* z, const double* pw, double* g, double* values) {
+  if (!p || !values) return fail(MPX_EINVAL, "NULL argument");
+  int rc = upload_inputs(*p, z, pw);
+  if (rc) return rc;
+  rc = launch_g_jac(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_g.as<double>(), p->d_vals.as<double>(), p->stream);
+  if (rc) return rc;
+  if (g) CUDA_TRY(cudaMemcpyAsync(g, p->d_g.p, (size_t)p->n_g * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(values, p->d_vals.p, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+extern "C" int mpx_eval_f(mpx_plan* p, const double* z, const double* pw, double* f) {
+  if (!p || !f) return fail(MPX_EINVAL, "NULL argument");
+  int rc = upload_inputs(*p, z, pw);
+  if (rc) return rc;
+  rc = launch_f_grad(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_f.as<double>(), nullptr, p->stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(f, p->d_f.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+extern "C" int mpx_eval_grad_f(mpx_plan* p, const double* z, const double* pw, double* f, double* grad) {
+  if (!p || !grad) return fail(MPX_EINVAL, "NULL argument");
+  int rc = upload_inputs(*p, z, pw);
+  if (rc) return rc;
+  rc = launch_f_grad(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_f.as<double>(), p->d_grad.as<double>(), p->stream);
+  if (rc) return rc;
+  if (f) CUDA_TRY(cudaMemcpyAsync(f, p->d_f.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(grad, p->d_grad.p, (size_t)p->n_z * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+extern "C" int mpx_eval_g_jac_dev(mpx_plan* p, const double* d_z, const double* d_p, double* d_g, double* d_values,
+                                  void* stream) {
+  if (!p || !d_z || !d_p || !d_g) return fail(MPX_EINVAL, "NULL argument");
+  return launch_g_jac(*p, d_z, d_p, d_g, d_values, stream ? (cudaStream_t)stream : p->stream);
+}
+
+extern "C" int mpx_eval_f_grad_dev(mpx_plan* p, const double* d_z, const double* d_p, double* d_f, double* d_grad,
+                                   void* stream) {
+  if (!p || !d_z || !d_p || !d_f) return fail(MPX_EINVAL, "NULL argument");
+  return launch_f_grad(*p, d_z, d_p, d_f, d_grad, stream ? (cudaStream_t)stream : p->stream);
+}
+
+extern "C" int mpx_sync(mpx_plan* p) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+extern "C" int64_t mpx_launch_count(const mpx_plan* p) { return p ? p->launches : 0; }
+extern "C" const char* mpx_program_origin(const mpx_plan* p) { return p ? p->origin.c_str() : ""; }

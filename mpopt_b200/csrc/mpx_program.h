@@ -1,0 +1,71 @@
+// mpx_program.h -- registry of compiled node-functor programs.
+//
+// A "program" is the set of kernels of csrc/mpx_kernels.cuh instantiated for the phase
+// functors generated from one traced OCP (mpopt_b200/program.py).  Programs compiled ahead
+// of time (csrc/gen/*.cu, built by __graft_entry__.build) register themselves here under
+// the hash of their generated source; programs compiled at run time through NVRTC
+// (csrc/mpx_plan.cu) implement the same interface.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "mpx_kernels.cuh"
+
+struct MpxPhaseKernels {
+  virtual ~MpxPhaseKernels() {}
+  virtual cudaError_t gjac(const MpxPhaseArgs& a, bool jac, int grid, size_t smem, cudaStream_t st) const = 0;
+  virtual cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const = 0;
+  virtual cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const = 0;
+};
+
+struct MpxProgramEntry {
+  const char* key;
+  int n_phases;
+  const MpxPhaseKernels* const* phases;
+  MpxProgramEntry* next;
+};
+
+extern "C" void mpx_register_program(MpxProgramEntry* e);
+const MpxProgramEntry* mpx_find_program(const char* key);
+
+// AOT implementation: direct <<<>>> launches of the template instantiations
+template <class PH>
+struct MpxAotPhase final : MpxPhaseKernels {
+  template <class K>
+  static cudaError_t allow_smem(K kern, size_t smem, bool& done) {
+    if (smem > 48 * 1024 && !done) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+    return cudaSuccess;
+  }
+  cudaError_t gjac(const MpxPhaseArgs& a, bool jac, int grid, size_t smem, cudaStream_t st) const override {
+    static bool d0 = false, d1 = false;
+    cudaError_t e;
+    if (jac) {
+      if ((e = allow_smem(mpx_gjac_kernel<PH, true>, smem, d1)) != cudaSuccess) return e;
+      mpx_gjac_kernel<PH, true><<<grid, MPX_THREADS, smem, st>>>(a);
+    } else {
+      if ((e = allow_smem(mpx_gjac_kernel<PH, false>, smem, d0)) != cudaSuccess) return e;
+      mpx_gjac_kernel<PH, false><<<grid, MPX_THREADS, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+  }
+  cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const override {
+    static bool d0 = false, d1 = false;
+    cudaError_t e;
+    if (grad) {
+      if ((e = allow_smem(mpx_fgrad_kernel<PH, true>, smem, d1)) != cudaSuccess) return e;
+      mpx_fgrad_kernel<PH, true><<<grid, MPX_THREADS, smem, st>>>(a);
+    } else {
+      if ((e = allow_smem(mpx_fgrad_kernel<PH, false>, smem, d0)) != cudaSuccess) return e;
+      mpx_fgrad_kernel<PH, false><<<grid, MPX_THREADS, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+  }
+  cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const override {
+    if (grad) mpx_fgrad_final<PH, true><<<1, 256, 0, st>>>(a);
+    else mpx_fgrad_final<PH, false><<<1, 256, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+};

@@ -1,0 +1,233 @@
+"""Host side of the transcribed NLP: traces the OCP, creates the device plan, exposes the evaluators.
+
+``Transcription`` is what ``mpopt.create_nlp`` + ``ca.nlpsol`` amount to in the reference
+(/root/reference/mpopt/mpopt.py:574-639, :725-758): it fixes the variable / constraint layout,
+the bounds (:546-570 and the ``*min/*max`` vectors of :234-519), the initial guess (:641-708) and
+owns the four evaluators ``f, grad_f, g, jac_g`` -- here CUDA kernels behind the C ABI of
+``include/mpx.h`` instead of CasADi's SX virtual machine.
+"""
+from __future__ import annotations
+
+import copy
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .program import Program
+
+
+def _u8(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.uint8).reshape(-1))
+
+
+class Transcription:
+    def __init__(self, ocp, n_segments=1, poly_orders=9, scheme="LGR", tau_min=-1.0, tau_max=1.0, device=0,
+                 drop_exact_zeros=True, segments=None, program=None):
+        if scheme not in _lib.SCHEMES:
+            raise ValueError(f"scheme must be one of {sorted(_lib.SCHEMES)} (got {scheme!r})")
+        self.ocp = copy.deepcopy(ocp)  # the reference snapshots the OCP too (mpopt.py:77)
+        self.K = int(n_segments)
+        self.poly_orders = [int(poly_orders)] * self.K if isinstance(poly_orders, (int, np.integer)) else \
+            [int(v) for v in poly_orders]
+        if len(self.poly_orders) != self.K:
+            raise AssertionError("len(poly_orders) must equal n_segments")  # mpopt.py:83
+        self.scheme, self.tau0, self.tau1 = scheme, float(tau_min), float(tau_max)
+        o = self.ocp
+        self.nx, self.nu, self.na, self.P = o.nx, o.nu, o.na, o.n_phases
+        self.N = sum(self.poly_orders) + 1  # mpopt.py:84
+        self.program = program if program is not None else Program(o)
+        self.device = int(device)
+
+        # ---- description handed over the C ABI (arrays kept alive on self)
+        L = _lib.lib()
+        self._keep = []
+        phases = (_lib.PhaseDesc * self.P)()
+        self.has_mU = []
+        for ph, pp in enumerate(self.program.phases):
+            mid = bool(o.midu[ph]) and bool((np.asarray(o.lbu[ph]) > -np.inf).any() or
+                                            (np.asarray(o.ubu[ph]) < np.inf).any())  # mpopt.py:346, :363-365
+            self.has_mU.append(mid)
+            arrs = [_u8(pp.pat_f()), _u8(pp.f_nz), _u8(pp.f_t()), _u8(pp.pat_c()), _u8(pp.c_t()), _u8(pp.pat_tc())]
+            self._keep += arrs
+            d = phases[ph]
+            d.n_path, d.n_term = pp.nc, pp.ntc
+            d.pat_f, d.f_nz, d.f_t, d.pat_c, d.c_t, d.pat_tc = [_lib.ptr(a, _lib.c_u8p) for a in arrs]
+            d.diff_u, d.midu = int(bool(o.diff_u[ph])), int(mid)
+            d.du_continuity = int(bool(o.du_continuity[ph]))
+            d.cost_t = int(not pp.Lt.is_value(0.0))
+        po = np.asarray(self.poly_orders, dtype=np.int32)
+        sx, su, sa = (np.ascontiguousarray(np.asarray(v, dtype=float)) for v in (o.scale_x, o.scale_u, o.scale_a))
+        links = np.asarray(o.phase_links if self.P > 1 else [], dtype=np.int32).reshape(-1)
+        self._keep += [po, sx, su, sa, links, phases]
+        desc = _lib.ProblemDesc()
+        desc.nx, desc.nu, desc.na, desc.n_phases = self.nx, self.nu, self.na, self.P
+        desc.phases = phases
+        desc.n_segments, desc.poly_orders = self.K, _lib.ptr(po, _lib.c_i32p)
+        desc.scheme, desc.tau_min, desc.tau_max = _lib.SCHEMES[scheme], self.tau0, self.tau1
+        desc.scale_x, desc.scale_u, desc.scale_a = _lib.ptr(sx), _lib.ptr(su), _lib.ptr(sa)
+        desc.scale_t = float(o.scale_t)
+        desc.n_links, desc.links = len(links) // 2, _lib.ptr(links, _lib.c_i32p)
+        desc.drop_exact_zeros = int(bool(drop_exact_zeros))
+        desc.program_key = self.program.key().encode()
+        desc.program_source = self.program.cuda_source().encode()
+        desc.device = self.device
+        desc.seg_begin, desc.seg_end = (0, 0) if segments is None else (int(segments[0]), int(segments[1]))
+        self.segments = (0, self.K) if segments is None else (int(segments[0]), int(segments[1]))
+        plan = C.c_void_p()
+        _lib.check(L.mpx_plan_create(C.byref(desc), C.byref(plan)))
+        self._plan, self._L = plan, L
+
+        s = [C.c_int64() for _ in range(4)]
+        _lib.check(L.mpx_sizes(plan, *[C.byref(v) for v in s]))
+        self.n_z, self.n_p, self.n_g, self.nnz = (int(v.value) for v in s)
+        self._structure = None
+
+    def __del__(self):
+        plan, self._plan = getattr(self, "_plan", None), None
+        if plan:
+            self._L.mpx_plan_destroy(plan)
+
+    # ------------------------------------------------------------------ structure / tables
+    def structure(self):
+        """(rowptr, colind) of jac_g, CSR, int64, sorted columns."""
+        if self._structure is None:
+            rp, ci = np.empty(self.n_g + 1, np.int64), np.empty(self.nnz, np.int64)
+            _lib.check(self._L.mpx_jac_structure(self._plan, _lib.ptr(rp, _lib.c_i64p), _lib.ptr(ci, _lib.c_i64p)))
+            self._structure = (rp, ci)
+        return self._structure
+
+    def structure_ccs(self):
+        """(colptr, rowind, perm): CasADi's column-compressed order; ccs_values = csr_values[perm]."""
+        cp, ri, pm = np.empty(self.n_z + 1, np.int64), np.empty(self.nnz, np.int64), np.empty(self.nnz, np.int64)
+        _lib.check(self._L.mpx_jac_structure_ccs(self._plan, *[_lib.ptr(a, _lib.c_i64p) for a in (cp, ri, pm)]))
+        return cp, ri, pm
+
+    def tables(self, deg):
+        n1 = deg + 1
+        r, D, w, Cm = np.empty(n1), np.empty((n1, n1)), np.empty(n1), np.empty((deg, n1))
+        _lib.check(self._L.mpx_plan_tables(self._plan, deg, *[_lib.ptr(a) for a in (r, D, w, Cm)]))
+        return r, D, w, Cm
+
+    def shard_runs(self, kind):
+        n = C.c_int64()
+        _lib.check(self._L.mpx_shard_runs(self._plan, kind, None, C.byref(n)))
+        runs = np.empty(2 * n.value, np.int64)
+        _lib.check(self._L.mpx_shard_runs(self._plan, kind, _lib.ptr(runs, _lib.c_i64p), C.byref(n)))
+        return runs.reshape(-1, 2)
+
+    # ------------------------------------------------------------------ evaluators (host buffers)
+    def _zp(self, z, p):
+        z = np.ascontiguousarray(z, dtype=float)
+        p = self.seg_width_params() if p is None else np.ascontiguousarray(p, dtype=float)
+        if z.shape != (self.n_z,) or p.shape != (self.n_p,):
+            raise ValueError(f"expected z of shape ({self.n_z},) and p of shape ({self.n_p},)")
+        return z, p
+
+    def f(self, z, p=None):
+        z, p = self._zp(z, p)
+        out = np.empty(1)
+        _lib.check(self._L.mpx_eval_f(self._plan, _lib.ptr(z), _lib.ptr(p), _lib.ptr(out)))
+        return float(out[0])
+
+    def grad_f(self, z, p=None, out=None):
+        z, p = self._zp(z, p)
+        out = np.empty(self.n_z) if out is None else out
+        _lib.check(self._L.mpx_eval_grad_f(self._plan, _lib.ptr(z), _lib.ptr(p), None, _lib.ptr(out)))
+        return out
+
+    def g(self, z, p=None, out=None):
+        z, p = self._zp(z, p)
+        out = np.empty(self.n_g) if out is None else out
+        _lib.check(self._L.mpx_eval_g(self._plan, _lib.ptr(z), _lib.ptr(p), _lib.ptr(out)))
+        return out
+
+    def jac_g_values(self, z, p=None, out=None, g_out=None):
+        z, p = self._zp(z, p)
+        out = np.empty(self.nnz) if out is None else out
+        _lib.check(self._L.mpx_eval_jac_g(self._plan, _lib.ptr(z), _lib.ptr(p), _lib.ptr(g_out), _lib.ptr(out)))
+        return out
+
+    def jac_g(self, z, p=None):
+        import scipy.sparse as sp
+
+        rp, ci = self.structure()
+        return sp.csr_matrix((self.jac_g_values(z, p), ci, rp), shape=(self.n_g, self.n_z))
+
+    # ------------------------------------------------------------------ evaluators (device pointers)
+    def g_jac_dev(self, z_ptr, p_ptr, g_ptr, vals_ptr, stream=None):
+        _lib.check(self._L.mpx_eval_g_jac_dev(self._plan, z_ptr, p_ptr, g_ptr, vals_ptr, stream))
+
+    def f_grad_dev(self, z_ptr, p_ptr, f_ptr, grad_ptr, stream=None):
+        _lib.check(self._L.mpx_eval_f_grad_dev(self._plan, z_ptr, p_ptr, f_ptr, grad_ptr, stream))
+
+    def sync(self):
+        _lib.check(self._L.mpx_sync(self._plan))
+
+    @property
+    def launches(self):
+        return int(self._L.mpx_launch_count(self._plan))
+
+    @property
+    def program_origin(self):
+        return self._L.mpx_program_origin(self._plan).decode()
+
+    # ------------------------------------------------------------------ bounds, parameters, initial guess
+    def seg_width_params(self):
+        """Equal segment widths summing to 1 per phase (mpopt.py:710-723)."""
+        return np.full(self.K * self.P, 1.0 / self.K)
+
+    def bounds(self):
+        """(Zmin, Zmax, Gmin, Gmax) in the layout of z and g."""
+        o, N, K, nx, nu = self.ocp, self.N, self.K, self.nx, self.nu
+        zlo, zhi, glo, ghi = [], [], [], []
+        for ph, pp in enumerate(self.program.phases):
+            xlo = np.repeat((np.asarray(o.lbx[ph], float) * o.scale_x)[:, None], N, axis=1)
+            xhi = np.repeat((np.asarray(o.ubx[ph], float) * o.scale_x)[:, None], N, axis=1)
+            if ph == 0:  # initial state pinned in phase 0 only (mpopt.py:550-551)
+                xlo[:, 0] = xhi[:, 0] = np.asarray(o.x00[0], float) * o.scale_x
+            ulo = np.repeat(np.asarray(o.lbu[ph], float) * o.scale_u, N)
+            uhi = np.repeat(np.asarray(o.ubu[ph], float) * o.scale_u, N)
+            zlo += [xlo.reshape(-1), ulo, np.atleast_1d(o.lbt0[ph] * o.scale_t), np.atleast_1d(o.lbtf[ph] * o.scale_t),
+                    np.asarray(o.lba[ph], float) * o.scale_a]
+            zhi += [xhi.reshape(-1), uhi, np.atleast_1d(o.ubt0[ph] * o.scale_t), np.atleast_1d(o.ubtf[ph] * o.scale_t),
+                    np.asarray(o.uba[ph], float) * o.scale_a]
+            glo += [np.full(nx * N, float(o.LB_DYNAMICS)), np.full(pp.nc * N, float(o.LB_PATH_CONSTRAINTS))]
+            ghi += [np.full(nx * N, float(o.UB_DYNAMICS)), np.full(pp.nc * N, float(o.UB_PATH_CONSTRAINTS))]
+            if o.diff_u[ph]:
+                glo.append(np.full(nu * N, float(o.lbdu[ph])))
+                ghi.append(np.full(nu * N, float(o.ubdu[ph])))
+            if self.has_mU[ph]:
+                glo.append(np.repeat(np.asarray(o.lbu[ph], float) * o.scale_u, N - 1))
+                ghi.append(np.repeat(np.asarray(o.ubu[ph], float) * o.scale_u, N - 1))
+            if o.du_continuity[ph] and K > 1:
+                glo.append(np.zeros(nu * (K - 1)))
+                ghi.append(np.zeros(nu * (K - 1)))
+            glo.append(np.full(pp.ntc, float(o.LB_TERMINAL_CONSTRAINTS)))
+            ghi.append(np.full(pp.ntc, float(o.UB_TERMINAL_CONSTRAINTS)))
+        if self.P > 1:
+            n = len(o.phase_links)
+            # the reference indexes lbe/ube by link ordinal, not by phase id (mpopt.py:491-497)
+            glo += [np.concatenate([np.asarray(o.lbe[i], float) * o.scale_x for i in range(n)]), np.zeros(n * nu),
+                    np.zeros(n)]
+            ghi += [np.concatenate([np.asarray(o.ube[i], float) * o.scale_x for i in range(n)]), np.zeros(n * nu),
+                    np.zeros(n)]
+        cat = lambda parts: np.concatenate([np.asarray(a, float).reshape(-1) for a in parts])
+        return cat(zlo), cat(zhi), cat(glo), cat(ghi)
+
+    def initial_guess(self):
+        """Linear interpolation between the OCP's start/end guesses (mpopt.py:641-708).
+
+        States are laid out state-major like z; controls come out node-major exactly as in the
+        reference (its quirk, SURVEY.md Q3 -- harmless unless nu > 1 and u00 != uf0)."""
+        o, N = self.ocp, self.N
+        parts = []
+        for ph in range(self.P):
+            x0, xf = np.asarray(o.x00[ph], float) * o.scale_x, np.asarray(o.xf0[ph], float) * o.scale_x
+            u0, uf = np.asarray(o.u00[ph], float) * o.scale_u, np.asarray(o.uf0[ph], float) * o.scale_u
+            ta, tb = float(np.ravel(o.t00[ph])[0]) * o.scale_t, float(np.ravel(o.tf0[ph])[0]) * o.scale_t
+            ts = np.linspace(ta, tb, N)
+            X = x0[None, :] + ((xf - x0) / (tb - ta))[None, :] * (ts - ta)[:, None]
+            U = u0[None, :] + ((uf - u0) / (tb - ta))[None, :] * (ts - ta)[:, None]
+            parts += [X.T.reshape(-1), U.reshape(-1), [ta], [tb], np.asarray(o.a0[ph], float) * o.scale_a]
+        return np.concatenate([np.asarray(a, float).reshape(-1) for a in parts])

