@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- fused residual + Jacobian (g + jac_g) evaluations per second of the collocation hot path.
+
+    python bench.py --gpus 1 --steps K --warmup W          this repo's CUDA path
+    python bench.py --impl reference ...                   the CPU restatement (oracle/) on the host cores
+    torchrun ... bench.py --gpus N ...                     segments sharded over N GPUs + NCCL all-gather
+
+A step is ONE fused g + jac_g evaluation of the transcribed NLP named by BASELINE.json's metric:
+seeded synthetic 6-state / 3-control OCP, n_segments=4096, poly_orders=15, LGR
+(n_z=552 971, n_g=552 966, nnz=12 533 916 -> 109.15 MB algorithmic bytes per evaluation).
+
+Prints one JSON line (see the task's bench contract): value = evaluations/s with inputs resident in HBM,
+e2e = the same through the host-pointer C ABI (mpx_eval_jac_g) with pinned host buffers, roofline =
+algorithmic bytes / CUDA-event time of the g+jac kernel against MEASURED_PEAKS.json, cpu_baseline = the
+oracle timed on this box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(problem="synthetic_6_3", n_segments=4096, poly_orders=15, scheme="LGR", tf=1.0)
+METRIC = "NLP residual+Jacobian evals/sec at n_seg=4096,p=15,nx=6"
+UNIT = "evals/s"
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only if MEASURED_PEAKS.json is absent
+
+
+def workload_point(n_z, n_p, K, seed=20261017, tf=1.0):
+    """Seeded inputs: X, U ~ U(-1,1); t0 = 0; tf; Dirichlet segment widths."""
+    rng = np.random.default_rng(seed)
+    z = rng.uniform(-1.0, 1.0, n_z)
+    z[-2:] = [0.0, tf]
+    p = rng.dirichlet(np.ones(K))
+    assert p.shape == (n_p,)
+    return z, p
+
+
+def algorithmic_bytes(n_z, n_p, n_g, nnz):
+    """read z and p once, write every g and every Jacobian value once."""
+    return 8 * (n_z + n_p + n_g + nnz)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed regions run."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self.nv, self.err = None, str(e)
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for name, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "samples": len(self.samples),
+                "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle)
+def _oracle_worker(args):
+    K, n_evals, seed = args
+    from mpopt_b200.problems import REGISTRY
+    from oracle.nlp import OracleNLP
+
+    ora = OracleNLP(REGISTRY[WORKLOAD["problem"]](), K, WORKLOAD["poly_orders"], WORKLOAD["scheme"])
+    z, p = workload_point(ora.n_z, ora.n_p, K, seed, WORKLOAD["tf"])
+    ora._eval(z, p)  # build caches
+    t = time.perf_counter()
+    for i in range(n_evals):
+        ora._eval(z + 1e-3 * i, p)
+    return time.perf_counter() - t
+
+
+def cpu_baseline(budget_s=20.0, cores=1):
+    """Time the oracle's fused g + jac_g on a bounded sample: the same problem at K_s <= 4096 segments, scaled
+    by K_s / 4096 (cost is linear in the number of segments).  Returns the cpu_baseline dict."""
+    import multiprocessing as mp
+
+    Kfull = WORKLOAD["n_segments"]
+    t1 = _oracle_worker((256, 1, 0))  # probe at 1/16 size
+    est_full = t1 * Kfull / 256
+    Ks = Kfull
+    while Ks > 256 and est_full * Ks / Kfull * 3 > budget_s:
+        Ks //= 2
+    n_evals = max(1, int(budget_s / max(est_full * Ks / Kfull, 1e-3) / 2))
+    n_evals = min(n_evals, 8)
+    if cores > 1:
+        with mp.get_context("fork").Pool(cores) as pool:
+            t0 = time.perf_counter()
+            pool.map(_oracle_worker, [(Ks, n_evals, s) for s in range(cores)])
+            wall = time.perf_counter() - t0
+        # wall includes building the oracle in every worker; conservative for the CPU side is to exclude it
+        per = max(pool_time for pool_time in [wall]) / n_evals
+        evals_per_s = cores / per
+    else:
+        per = _oracle_worker((Ks, n_evals, 0)) / n_evals
+        evals_per_s = 1.0 / per
+    value = evals_per_s * Ks / Kfull
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"numpy/scipy oracle, fused g+jac_g of the same OCP at n_segments={Ks} (x{Ks}/{Kfull} scaling), "
+                      f"{n_evals} evals per core, {os.cpu_count()} host cores present"}
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference's path on all host cores (the reference itself,
+    CasADi + IPOPT, cannot be installed in this image -- SURVEY.md 8c)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    steps, warmup = args.steps, args.warmup
+    budget = min(150.0, 2.0 * (steps + warmup))
+    cb = cpu_baseline(budget_s=max(10.0, budget), cores=cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(workload="synthetic 6-state/3-control OCP, n_segments=4096, poly_orders=15, LGR; "
+                                "fused g + jac_g", **{k: WORKLOAD[k] for k in ("n_segments", "poly_orders", "scheme")}),
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CasADi/IPOPT are not installable here; this is the numpy/scipy oracle port of mpopt.py's transcription",
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+def run_cuda(args):
+    import torch
+
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from mpopt_b200 import shard as sh
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    K = WORKLOAD["n_segments"]
+    ocp = REGISTRY[WORKLOAD["problem"]]()
+    part = sh.partition([WORKLOAD["poly_orders"]] * K, world)
+    seg = part[rank]
+    tr = Transcription(ocp, K, WORKLOAD["poly_orders"], WORKLOAD["scheme"], device=local,
+                       segments=None if world == 1 else seg)
+    n_z, n_p, n_g, nnz = tr.n_z, tr.n_p, tr.n_g, tr.nnz
+    B = algorithmic_bytes(n_z, n_p, n_g, nnz)
+    z_h, p_h = workload_point(n_z, n_p, K, tf=WORKLOAD["tf"])
+
+    # rotating device-resident input/output sets: R * (outputs) > L2 so every launch streams to HBM
+    R = 4
+    z_d = [torch.from_numpy(z_h + 1e-3 * i).to(dev) for i in range(R)]
+    p_d = torch.from_numpy(p_h).to(dev)
+    g_d = [torch.empty(n_g, dtype=torch.float64, device=dev) for _ in range(R)]
+    v_d = [torch.empty(nnz, dtype=torch.float64, device=dev) for _ in range(R)]
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+
+    gather = None
+    if world > 1:
+        gather = sh.Gatherer(tr, part, dist, dev)
+
+    def step(i):
+        k = i % R
+        tr.g_jac_dev(z_d[k].data_ptr(), p_d.data_ptr(), g_d[k].data_ptr(), v_d[k].data_ptr(), sp)
+        if gather is not None:
+            gather.all_gather(g_d[k], v_d[k])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+
+    # ---- timed region A (primary): K back-to-back steps over rotating buffer sets, one event pair
+    l0 = tr.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    launches = tr.launches - l0
+    ms_total = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+
+    # ---- timed region B (kernel alone, L2 flushed before every launch): roofline numerator
+    kern_ms = []
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i, (a, b) in enumerate(ev):
+        flush.fill_(float(i))
+        a.record(stream)
+        tr.g_jac_dev(z_d[i % R].data_ptr(), p_d.data_ptr(), g_d[i % R].data_ptr(), v_d[i % R].data_ptr(), sp)
+        b.record(stream)
+    torch.cuda.synchronize()
+    kern_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    shard_bytes = B if world == 1 else 8 * (n_z + n_p + sum(c for _, c in tr.shard_runs(0)) + sum(c for _, c in tr.shard_runs(1)))
+
+    # ---- end-to-end: host buffers through the C ABI (pinned), H2D of z/p and D2H of g/values inside the timing
+    e2e = None
+    if world == 1:
+        zh = torch.from_numpy(z_h.copy()).pin_memory()
+        ph_ = torch.from_numpy(p_h.copy()).pin_memory()
+        gh = torch.empty(n_g, dtype=torch.float64).pin_memory()
+        vh = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        n_e2e = max(3, min(args.steps, 50))
+        for _ in range(2):
+            tr.jac_g_values(zh.numpy(), ph_.numpy(), out=vh.numpy(), g_out=gh.numpy())
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            zh[0] = float(z_h[0] + 1e-6 * i)
+            tr.jac_g_values(zh.numpy(), ph_.numpy(), out=vh.numpy(), g_out=gh.numpy())
+        dt = (time.perf_counter() - t0) / n_e2e
+        e2e = {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * (n_z + n_p), "d2h_bytes_per_step": 8 * (n_g + nnz),
+               "ms_per_step": dt * 1e3, "steps": n_e2e, "api": "mpx_eval_jac_g (host pointers, pinned buffers)"}
+    sampler.stop_flag = True
+    sampler.join(timeout=1.0)
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+    kmed = float(np.median(kern_ms))
+    achieved = shard_bytes / (kmed * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    cb = cpu_baseline(budget_s=args.cpu_budget, cores=1) if not args.no_cpu else None
+    line = {
+        "metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "synthetic 6-state/3-control quadratic-dynamics OCP (SURVEY 8d), n_segments=4096, "
+                               "poly_orders=15, LGR: one fused g + jac_g evaluation per step",
+                   "n_z": n_z, "n_g": n_g, "nnz_jac": nnz, "algorithmic_bytes": B,
+                   "l2": f"value: {R} rotating z/g/values sets ({R * B / 1e6:.0f} MB > 126 MB L2), launches back to back; "
+                         "roofline: L2 flushed (256 MB fill) before every timed launch",
+                   "parallelism": "1 GPU" if world == 1 else f"segments sharded over {world} GPUs + NCCL all-gather of g/values",
+                   "program": tr.program_origin},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "mpx_gjac_kernel<synthetic_6_3, JAC>",
+                     "kernel_us_median": kmed * 1e3, "kernel_us_min": float(kern_ms.min()) * 1e3,
+                     "bytes_per_launch": shard_bytes},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
+    }
+    if cb is not None:
+        line["cpu_baseline"] = cb
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -74,16 +74,31 @@ def _nvcc():
     return nvcc
 
 
+def _digest(src):
+    """Content hash of a source and of every header it can include (mtimes do not survive a snapshot copy)."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = [src] + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    deps.append(os.path.join(HERE, "..", "include", "mpx.h"))
+    for d in deps:
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _compile(src, force):
     obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps.append(os.path.join(HERE, "..", "include", "mpx.h"))
-    if not force and os.path.exists(obj) and all(os.path.getmtime(obj) >= os.path.getmtime(d) for d in deps):
-        return obj, ""
+    stamp = obj + ".sha"
+    dig = _digest(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == dig:
+        return obj, None
     cmd = [_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+    with open(stamp, "w") as f:
+        f.write(dig)
     return obj, r.stderr
 
 
@@ -94,11 +109,11 @@ def build(force=False, verbose=False):
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         results = list(ex.map(lambda s: _compile(s, force), srcs))
     objs = [o for o, _ in results]
-    log = "".join(l for _, l in results)
-    if log:
-        with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
-            f.write(log)
-    if force or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+    rebuilt = [l for _, l in results if l is not None]
+    if rebuilt:
+        with open(os.path.join(OBJ, "ptxas.log"), "a" if len(rebuilt) < len(results) else "w") as f:
+            f.write("".join(rebuilt))
+    if force or rebuilt or not os.path.exists(LIB):
         cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

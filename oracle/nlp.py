@@ -33,7 +33,7 @@ def _const_or_dual(v, n):
 
 class OracleNLP:
     def __init__(self, ocp, n_segments=1, poly_orders=9, scheme="LGR", tau_min=-1.0, tau_max=1.0,
-                 drop_exact_zeros=True):
+                 drop_exact_zeros=True, tables=None):
         # mpopt.py:56-93
         self.K = int(n_segments)
         self.po = [poly_orders] * self.K if isinstance(poly_orders, (int, np.integer)) else list(poly_orders)
@@ -41,7 +41,7 @@ class OracleNLP:
         self.ocp = copy.deepcopy(ocp)  # :77 (Q9)
         self.scheme = scheme
         self.N = sum(self.po) + 1  # :84
-        self.tab = Tables(self.po, scheme, tau_min, tau_max)  # :95-103
+        self.tab = Tables(self.po, scheme, tau_min, tau_max, override=tables)  # :95-103
         self.tau0, self.tau1 = self.tab.tau0, self.tab.tau1
         self.drop = bool(drop_exact_zeros)
         o = self.ocp
@@ -51,16 +51,15 @@ class OracleNLP:
         self.n_p = self.K * self.P  # :152, :631
         # node ownership, :189-195 -- a shared boundary node is the LAST point of the earlier segment
         self.seg_start = np.concatenate([[0], np.cumsum(self.po)[:-1]]).astype(np.int64)
-        seg = np.zeros(self.N, dtype=np.int64)
-        loc = np.zeros(self.N, dtype=np.int64)
-        for k, p in enumerate(self.po):
-            s = self.seg_start[k]
-            lo = 0 if k == 0 else 1
-            seg[s + lo: s + p + 1] = k
-            loc[s + lo: s + p + 1] = np.arange(lo, p + 1)
+        po = np.asarray(self.po, dtype=np.int64)
+        seg = np.concatenate([[0], np.repeat(np.arange(self.K), po)]).astype(np.int64)
+        loc = np.arange(self.N) - self.seg_start[seg]
         self.node_seg, self.node_loc = seg, loc
         # tau of every node inside its owning segment, minus tau0 (:198)
-        self.node_dtau = np.array([self.tab.roots[self.po[k]][l] - self.tau0 for k, l in zip(seg, loc)])
+        self.node_dtau = np.zeros(self.N)
+        for d in set(self.po):
+            m = po[seg] == d
+            self.node_dtau[m] = self.tab.roots[d][loc[m]] - self.tau0
         # constant composite matrices
         self._compD = self._maybe_drop(self.tab.composite_D())  # :99
         self._compW = self.tab.composite_W()  # :100

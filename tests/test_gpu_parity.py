@@ -29,34 +29,52 @@ CASES = [
 ]
 
 
-def _build(problem, K, po, scheme, drop=True):
-    from mpopt_b200.nlp import Transcription
+def _ocp(problem, scheme):
     from mpopt_b200.problems import REGISTRY
-    from oracle.nlp import OracleNLP
 
     ocp = REGISTRY[problem]()
     if problem == "moon_lander" and scheme == "LGL":
         ocp.diff_u[0], ocp.du_continuity[0] = 1, 1
-    ora = OracleNLP(ocp, K, po, scheme, drop_exact_zeros=drop)
+    return ocp
+
+
+def _build(problem, K, po, scheme, drop=True, device_tables=False):
+    """(oracle, Transcription).  With ``device_tables`` the oracle is handed the plan's own tables (checked
+    against the oracle's to <= 1e-11 first) so that the exact-zero folding (Q10), which hinges on rounding
+    noise in analytically-zero entries, is decided on identical numbers."""
+    from mpopt_b200.nlp import Transcription
+    from oracle.nlp import OracleNLP
+
+    ocp = _ocp(problem, scheme)
     tr = Transcription(ocp, K, po, scheme, drop_exact_zeros=drop)
+    ora = OracleNLP(ocp, K, po, scheme, drop_exact_zeros=drop)
+    if device_tables:
+        tabs = {}
+        for d in sorted(set(tr.poly_orders)):
+            r, D, w, Cm = tr.tables(d)
+            assert_close(r, ora.tab.roots[d], f"roots[{d}]", 1e-13)
+            assert_close(D, ora.tab.D[d], f"D[{d}]", 1e-11)
+            assert_close(w, ora.tab.w[d], f"w[{d}]", 1e-13)
+            assert_close(Cm, ora.tab.Cmid[d], f"Cmid[{d}]", 1e-12)
+            tabs[d] = (r, D, w, Cm)
+        ora = OracleNLP(ocp, K, po, scheme, drop_exact_zeros=drop, tables=tabs)
     return ora, tr
+
+
+def _point(ora, problem, dirichlet):
+    z, p = random_point(ora, dirichlet=dirichlet)
+    if problem == "robot_arm":
+        z = np.abs(z) + 0.5  # keep sin(x4) and the inertia terms away from zero
+    return z, p
 
 
 @pytest.mark.parametrize("name,problem,K,po,scheme,dirichlet", CASES, ids=[c[0] for c in CASES])
 def test_g_jac_f_grad_match_oracle(libmpx, name, problem, K, po, scheme, dirichlet):
-    ora, tr = _build(problem, K, po, scheme)
+    """Fully independent comparison: oracle tables from scipy, every structural entry kept."""
+    ora, tr = _build(problem, K, po, scheme, drop=False)
     assert (tr.n_z, tr.n_p, tr.n_g) == (ora.n_z, ora.n_p, ora.n_g)
     assert tr.program_origin.startswith("aot:")
-    z, p = random_point(ora, dirichlet=dirichlet)
-    if problem == "robot_arm":
-        z = np.abs(z) + 0.5  # keep sin(x4) and the inertia terms away from zero
-    # tables first: structure masks depend on their exact zeros
-    for d in sorted(set(tr.poly_orders)):
-        r, D, w, Cm = tr.tables(d)
-        assert_close(r, ora.tab.roots[d], f"roots[{d}]", 1e-13)
-        assert_close(D, ora.tab.D[d], f"D[{d}]", 1e-11)
-        assert_close(w, ora.tab.w[d], f"w[{d}]", 1e-13)
-        assert_close(Cm, ora.tab.Cmid[d], f"Cmid[{d}]", 1e-12)
+    z, p = _point(ora, problem, dirichlet)
     rp, ci = tr.structure()
     J = ora.jac_g(z, p)
     assert np.array_equal(rp, J.indptr.astype(np.int64)), "rowptr differs"
@@ -73,9 +91,24 @@ def test_g_jac_f_grad_match_oracle(libmpx, name, problem, K, po, scheme, dirichl
     assert_close(tr.jac_g_values(z2, p), ora.jac_g(z2, p).data, "jac_g values (2nd point)")
 
 
+@pytest.mark.parametrize("name,problem,K,po,scheme,dirichlet", CASES, ids=[c[0] for c in CASES])
+def test_folded_pattern_matches_oracle(libmpx, name, problem, K, po, scheme, dirichlet):
+    """Default mode (exact-zero table entries folded away like CasADi's SX does): tables agree with the
+    oracle's, then structure is bit-exact and values agree on the folded pattern."""
+    ora, tr = _build(problem, K, po, scheme, drop=True, device_tables=True)
+    z, p = _point(ora, problem, dirichlet)
+    rp, ci = tr.structure()
+    J = ora.jac_g(z, p)
+    assert np.array_equal(rp, J.indptr.astype(np.int64)), "rowptr differs"
+    assert np.array_equal(ci, J.indices.astype(np.int64)), "colind differs"
+    g = np.empty(tr.n_g)
+    assert_close(tr.jac_g_values(z, p, g_out=g), J.data, "jac_g values")
+    assert_close(g, ora.g(z, p), "g")
+
+
 def test_golden_G0_structure(libmpx):
     """SURVEY.md Appendix A golden: moon-lander, LGR, K=2, poly_orders=[2,1]."""
-    _, tr = _build("moon_lander", 2, [2, 1], "LGR")
+    _, tr = _build("moon_lander", 2, [2, 1], "LGR", drop=False)
     rp, ci = tr.structure()
     assert (tr.n_z, tr.n_g, tr.nnz) == (14, 13, 56)
     assert rp.tolist() == [0, 6, 12, 18, 23, 29, 35, 41, 46, 49, 52, 54, 55, 56]
@@ -85,7 +118,7 @@ def test_golden_G0_structure(libmpx):
 
 
 def test_ccs_adapter(libmpx):
-    ora, tr = _build("two_phase_schwartz", 4, 5, "LGR")
+    ora, tr = _build("two_phase_schwartz", 4, 5, "LGR", device_tables=True)
     z, p = random_point(ora)
     cp, ri, perm = tr.structure_ccs()
     Jc = ora.jac_g(z, p).tocsc()
@@ -94,13 +127,14 @@ def test_ccs_adapter(libmpx):
     assert_close(tr.jac_g_values(z, p)[perm], Jc.data, "CCS values")
 
 
-def test_keep_exact_zeros_mode(libmpx):
-    ora, tr = _build("van_der_pol", 3, 4, "LGL", drop=False)
-    z, p = random_point(ora)
-    J = ora.jac_g(z, p)
-    rp, ci = tr.structure()
-    assert np.array_equal(rp, J.indptr) and np.array_equal(ci, J.indices)
-    assert_close(tr.jac_g_values(z, p), J.data, "values (drop_exact_zeros=False)")
+def test_exact_zero_folding_changes_pattern(libmpx):
+    """LGL interior diagonal entries are analytically 0; whichever come out exactly 0.0 leave the pattern."""
+    ora, tr = _build("van_der_pol", 3, 4, "LGL", drop=True, device_tables=True)
+    _, tr_full = _build("van_der_pol", 3, 4, "LGL", drop=False)
+    D = tr.tables(4)[1]
+    assert tr.nnz <= tr_full.nnz
+    if D[2, 2] == 0.0:  # centre node of a symmetric 5-point rule
+        assert tr.nnz < tr_full.nnz
 
 
 def test_config2_size_properties(libmpx):
@@ -134,7 +168,8 @@ def test_headline_counts(libmpx):
     assert (tr.n_z, tr.n_g, tr.nnz) == (552971, 552966, 12533916)
     from oracle.nlp import OracleNLP
 
-    ora = OracleNLP(synthetic_6_3(), 4096, 15, "LGR")
+    tabs = {15: tr.tables(15)}
+    ora = OracleNLP(synthetic_6_3(), 4096, 15, "LGR", tables=tabs)
     z, p = random_point(ora, tf=1.0, dirichlet=True)
     J = ora.jac_g(z, p)
     rp, ci = tr.structure()
