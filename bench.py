@@ -193,15 +193,23 @@ def run_cuda(args):
     g_d = [torch.empty(n_g, dtype=torch.float64, device=dev) for _ in range(R)]
     v_d = [torch.empty(nnz, dtype=torch.float64, device=dev) for _ in range(R)]
     flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a real (non-NULL) stream: events and kernels share it (NULL = plan's own stream)
+    torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
+    assert sp != 0
 
     gather = None
     if world > 1:
-        gather = sh.Gatherer(tr, part, dist, dev)
+        row0 = None
+        if rank != 0:  # global node 0's rows are recomputed locally instead of being broadcast (mpopt_b200/shard.py)
+            tr0 = Transcription(ocp, K, WORKLOAD["poly_orders"], WORKLOAD["scheme"], device=local, segments=(0, 1))
+            row0 = lambda g, v: tr0.g_jac_dev(z_cur[0].data_ptr(), p_d.data_ptr(), g.data_ptr(), v.data_ptr(), sp)
+        gather = sh.Gatherer(tr.layout, part, dist, rank, dev, row0)
+    z_cur = [None]
 
     def step(i):
         k = i % R
+        z_cur[0] = z_d[k]
         tr.g_jac_dev(z_d[k].data_ptr(), p_d.data_ptr(), g_d[k].data_ptr(), v_d[k].data_ptr(), sp)
         if gather is not None:
             gather.all_gather(g_d[k], v_d[k])

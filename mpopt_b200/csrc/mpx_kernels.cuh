@@ -48,11 +48,15 @@ struct MpxPhaseArgs {
   double* grad;             // fgrad only
   double* partial;          // fgrad only: [K][MPX_NPART] per-segment partial sums
   double* fout;             // fgrad final: objective
+  const int32_t* unit_k;    // v2: first segment of each work unit (adjacent segments of equal degree)
+  const int32_t* unit_n;    // v2: number of segments in the unit (<= 32 / pow2ceil(degree+1))
   int32_t K, N, seg_begin, seg_end;
   int32_t uniform_deg;
   int32_t flags;
   int32_t accumulate_f;     // fgrad final: add to *fout instead of overwriting (phases > 0)
-  int32_t pad_;
+  int32_t n_units;          // v2
+  int32_t tab_doubles;      // v2: size of all table records (copied to shared memory once per CTA)
+  int32_t stage_cap;        // v2: staging doubles per warp
   int64_t zoff;             // offset of this phase in z
   int64_t gF, gC, gDU, gmU, gTC;       // first row of each block
   int64_t vF[MPX_MAXS], vC[MPX_MAXS];  // value offset of the first F row of state s / path row q
@@ -64,14 +68,17 @@ struct MpxPhaseArgs {
 
 // table record of one degree d (n1 = d+1), all sections padded to an even number of doubles so
 // the whole record is one 16-byte-granular bulk copy:
-//   roots[n1] | w[n1] | D[n1*n1] row-major | Cmid[d*n1] row-major
+//   roots[n1] | w[n1] | D[n1*n1] row-major | Cmid[d*n1] row-major | Dt[n1*n1] = D^T | Ct[n1*d] = Cmid^T
+// (the transposed copies give conflict-free shared-memory reads when lane = row)
 struct MpxTab {
   MPX_HD static int pad2(int n) { return (n + 1) & ~1; }
   MPX_HD static int off_roots(int) { return 0; }
   MPX_HD static int off_w(int n1) { return pad2(n1); }
   MPX_HD static int off_D(int n1) { return 2 * pad2(n1); }
   MPX_HD static int off_C(int n1) { return 2 * pad2(n1) + pad2(n1 * n1); }
-  MPX_HD static int size(int n1) { return 2 * pad2(n1) + pad2(n1 * n1) + pad2((n1 - 1) * n1); }
+  MPX_HD static int off_Dt(int n1) { return off_C(n1) + pad2((n1 - 1) * n1); }
+  MPX_HD static int off_Ct(int n1) { return off_Dt(n1) + pad2(n1 * n1); }
+  MPX_HD static int size(int n1) { return off_Ct(n1) + pad2((n1 - 1) * n1); }
 };
 
 #define MPX_NPART (3 + MPX_MAXS)  // J, dJ/dT0, dJ/dTF, dJ/da_m
@@ -435,6 +442,259 @@ __global__ void __launch_bounds__(MPX_THREADS) mpx_gjac_kernel(const __grid_cons
           if (PH::jtc_row(e) == r) A.vals[A.vTC + off + PH::jtc_pos(e)] = jtc[e] * mpx_iscale_term<PH>(A, PH::jtc_var(e));
       }
       off += PH::tc_len(r);
+    }
+  }
+}
+
+// =====================================================================================
+// K2 (v2): persistent warps.  Each warp repeatedly takes a work unit = up to 32/LW adjacent
+// segments of equal degree d (LW = pow2ceil(d+1)); lane = (segment q, local node r).  The
+// tables of every degree stay resident in shared memory (one bulk TMA copy per CTA), the
+// constant D blocks are pre-staged once per (degree) and only the z-dependent entries are
+// rewritten per unit; the rows of a unit are contiguous in CSR order, so each state is one
+// coalesced 16-byte-store stream.  No block-level barrier after start-up.
+// =====================================================================================
+#define MPX2_MAX_THREADS 256
+
+template <class PH>
+__device__ __forceinline__ int mpx2_region(int rows_cap, int n1, int s_end, int q_end) {
+  int off = 0;
+#pragma unroll
+  for (int s = 0; s < PH::NX; ++s)
+    if (s < s_end) off += rows_cap * (n1 + PH::f_next(s));
+#pragma unroll
+  for (int q = 0; q < PH::NC; ++q)
+    if (q < q_end) off += rows_cap * PH::c_len(q);
+  return off;
+}
+
+template <class PH, bool JAC>
+__global__ void __launch_bounds__(MPX2_MAX_THREADS, 1) mpx_gjac2_kernel(const __grid_constant__ MpxPhaseArgs A) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int NX = PH::NX, NU = PH::NU, NA = PH::NA, NC = PH::NC, NV = PH::NX + PH::NU;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  double* sTab = smem;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sTab + A.tab_doubles);
+  double* wbase = sTab + A.tab_doubles + 2 + (size_t)warp * (32 * NV + (JAC ? A.stage_cap : 0));
+  double* sXU = wbase;            // [q][v][LW]
+  double* stage = wbase + 32 * NV;
+  if (threadIdx.x == 0) {
+    mpx_mbar_init(bar, 1);
+    const uint32_t bytes = (uint32_t)A.tab_doubles * 8u;
+    mpx_mbar_expect_tx(bar, bytes);
+    mpx_tma_load_1d(sTab, A.tabs, bytes, bar);
+  }
+  const double* zp = A.z + A.zoff;
+  const int64_t zt = (int64_t)NV * A.N;
+  const double T0 = zp[zt], TF = zp[zt + 1];
+  const double t0 = T0 / A.st, tf = TF / A.st;  // mpopt.py:175-176
+  double a[NA > 0 ? NA : 1];
+#pragma unroll
+  for (int m = 0; m < NA; ++m) a[m] = zp[zt + 2 + m] * A.isa[m];
+  __syncthreads();
+  mpx_mbar_wait(bar, 0);
+
+  int cur_sig = -1;
+  const int tw = gridDim.x * nwarps;
+  for (int u = blockIdx.x * nwarps + warp; u < A.n_units; u += tw) {
+    const int k0 = A.unit_k[u], cnt = A.unit_n[u];
+    const MpxSeg S0 = mpx_segment(A, k0);
+    const double* tab = sTab + (S0.tab - A.tabs);
+    const int d = S0.d, n1 = d + 1;
+    const int shift = 32 - __clz(d);          // LW = pow2ceil(d+1)
+    const int LW = 1 << shift, smax = 32 >> shift;
+    const int q = lane >> shift, r = lane & (LW - 1);
+    const int has0 = k0 == 0 ? 1 : 0;
+    const bool inseg = q < cnt && r <= d;
+    const int rb = (has0 && q == 0) ? 0 : 1;
+    const bool owner = inseg && r >= rb;       // a shared node belongs to the earlier segment (mpopt.py:189-195)
+    const int row = (q == 0 ? 0 : q * d + has0) + r - rb;
+    const int rows_total = cnt * d + has0, rows_cap = smax * d + 1;
+    const int s0q = S0.s0 + q * d;
+    const double* sD = tab + MpxTab::off_D(n1);
+    const double* sDt = tab + MpxTab::off_Dt(n1);
+
+    // ---- constant D blocks: staged once per (degree, first-unit) signature
+    if (JAC && cur_sig != d * 2 + has0) {
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < NX; ++s) {
+        const int Ls = n1 + PH::f_next(s);
+        double* reg = stage + mpx2_region<PH>(rows_cap, n1, s, 0) + PH::f_npre(s);
+        for (int qq = 0; qq < smax; ++qq) {
+          const int rbq = (has0 && qq == 0) ? 0 : 1;
+          const int rowb = (qq == 0 ? 0 : qq * d + has0) - rbq;
+          for (int rr = rbq + q; rr <= d; rr += smax)
+            if (r <= d && !(PH::f_diag(s) >= 0 && r == rr)) reg[(rowb + rr) * Ls + r] = sD[rr * n1 + r];
+        }
+      }
+      cur_sig = d * 2 + has0;
+    }
+
+    // ---- this lane's node: coalesced loads from the state-major decision vector
+    double x[NX > 0 ? NX : 1], uu[NU > 0 ? NU : 1];
+    if (inseg) {
+#pragma unroll
+      for (int s = 0; s < NX; ++s) {
+        const double val = zp[(int64_t)s * A.N + s0q + r];
+        sXU[((q * NV + s) << shift) + r] = val;
+        x[s] = val * A.isx[s];
+      }
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        const double val = zp[(int64_t)(NX + c) * A.N + s0q + r];
+        sXU[((q * NV + NX + c) << shift) + r] = val;
+        uu[c] = val * A.isu[c];
+      }
+    }
+    __syncwarp();
+    const double* xq = sXU + ((q * NV) << shift);
+    const int kk = k0 + (q < cnt ? q : 0);
+    const double wk = A.w[kk];
+    const double h = (tf - t0) / A.delta * wk;  // mpopt.py:184
+    const double gk = wk / (A.delta * A.st);
+
+    if (owner) {
+      double sigma = 0.0, t = t0;
+      if (PH::F_T || PH::C_T) {
+        const double dt = tab[MpxTab::off_roots(n1) + r] - A.tau0;
+        sigma = A.sig0[kk] + wk * dt / A.delta;
+        t = (t0 + (tf - t0) * A.sig0[kk]) + h * dt;  // mpopt.py:192, :198
+      }
+      {
+        double f[NX > 0 ? NX : 1], jf[PH::NJF > 0 ? PH::NJF : 1], ft[NX > 0 ? NX : 1];
+        PH::dyn(x, uu, t, a, f, jf, ft);
+        if (JAC) {
+#pragma unroll
+          for (int s = 0; s < NX; ++s) {
+            const int Ls = n1 + PH::f_next(s);
+            double* rowp = stage + mpx2_region<PH>(rows_cap, n1, s, 0) + row * Ls;
+#pragma unroll
+            for (int e = 0; e < PH::NJF; ++e) {
+              if (PH::jf_row(e) != s) continue;
+              const double val = -h * (A.sx[s] * mpx_iscale<PH>(A, PH::jf_var(e))) * jf[e];
+              const int pos = PH::jf_pos(e);
+              if (pos < 0) rowp[PH::f_npre(s) + r] = sD[r * n1 + r] + val;
+              else rowp[pos < PH::f_npre(s) ? pos : pos + n1] = val;
+            }
+            if (PH::f_nz(s)) {
+              const int tp = PH::f_tpos(s) + n1;
+              const double a1 = gk * A.sx[s] * f[s];
+              const double a2 = PH::F_T ? h * A.sx[s] * ft[s] / A.st : 0.0;
+              rowp[tp] = a1 - a2 * (1.0 - sigma);
+              rowp[tp + 1] = -a1 - a2 * sigma;
+            }
+          }
+        }
+        // defect rows F = D.X - h Sx f (mpopt.py:232); lane = row, D^T gives conflict-free reads
+        double acc[NX > 0 ? NX : 1];
+#pragma unroll
+        for (int s = 0; s < NX; ++s) acc[s] = 0.0;
+        for (int j = 0; j < n1; ++j) {
+          const double dj = sDt[j * n1 + r];
+#pragma unroll
+          for (int s = 0; s < NX; ++s) acc[s] = fma(dj, xq[(s << shift) + j], acc[s]);
+        }
+#pragma unroll
+        for (int s = 0; s < NX; ++s) A.g[A.gF + (int64_t)s * A.N + s0q + r] = acc[s] - h * A.sx[s] * f[s];
+      }
+      if (NC > 0) {
+        double c[NC > 0 ? NC : 1], jc[PH::NJC > 0 ? PH::NJC : 1], ct[NC > 0 ? NC : 1];
+        PH::path(x, uu, t, a, c, jc, ct);
+#pragma unroll
+        for (int qc = 0; qc < NC; ++qc) A.g[A.gC + (int64_t)qc * A.N + s0q + r] = c[qc];  // mpopt.py:204
+        if (JAC) {
+#pragma unroll
+          for (int qc = 0; qc < NC; ++qc) {
+            const int Lq = PH::c_len(qc);
+            double* rowp = stage + mpx2_region<PH>(rows_cap, n1, NX, qc) + row * Lq;
+#pragma unroll
+            for (int e = 0; e < PH::NJC; ++e) {
+              if (PH::jc_row(e) != qc) continue;
+              rowp[PH::jc_pos(e)] = jc[e] * mpx_iscale<PH>(A, PH::jc_var(e));
+            }
+            if (PH::c_tpos(qc) >= 0) {
+              rowp[PH::c_tpos(qc)] = ct[qc] * (1.0 - sigma) / A.st;
+              rowp[PH::c_tpos(qc) + 1] = ct[qc] * sigma / A.st;
+            }
+          }
+        }
+      }
+      if (A.flags & MPX_F_DU) {  // control slope rows (mpopt.py:315-324)
+        double acc[NU > 0 ? NU : 1];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) acc[c] = 0.0;
+        for (int j = 0; j < n1; ++j) {
+          const double dj = sDt[j * n1 + r];
+#pragma unroll
+          for (int c = 0; c < NU; ++c) acc[c] = fma(dj, xq[((NX + c) << shift) + j], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NU; ++c) A.g[A.gDU + (int64_t)c * A.N + s0q + r] = acc[c];
+      }
+      // terminal constraint rows (mpopt.py:277-292) by the lane that owns the last node
+      if ((A.flags & MPX_F_TAIL) && PH::NTC > 0 && kk == A.K - 1 && r == d) {
+        double x0[NX > 0 ? NX : 1];
+#pragma unroll
+        for (int s = 0; s < NX; ++s) x0[s] = zp[(int64_t)s * A.N] * A.isx[s];
+        double tc[PH::NTC > 0 ? PH::NTC : 1], jtc[PH::NJTC > 0 ? PH::NJTC : 1], M[1], gm[PH::NGM > 0 ? PH::NGM : 1];
+        PH::term(x, tf, x0, t0, a, tc, jtc, M, gm);
+        int off = 0;
+#pragma unroll
+        for (int rr = 0; rr < PH::NTC; ++rr) {
+          A.g[A.gTC + rr] = tc[rr];
+          if (JAC) {
+#pragma unroll
+            for (int e = 0; e < PH::NJTC; ++e)
+              if (PH::jtc_row(e) == rr)
+                A.vals[A.vTC + off + PH::jtc_pos(e)] = jtc[e] * mpx_iscale_term<PH>(A, PH::jtc_var(e));
+          }
+          off += PH::tc_len(rr);
+        }
+      }
+    }
+    // mid-point control rows (mpopt.py:350-369): lane r < d is mid-point r of its segment
+    if ((A.flags & MPX_F_MU) && inseg && r < d) {
+      const double* sCt = tab + MpxTab::off_Ct(n1);
+      double acc[NU > 0 ? NU : 1];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) acc[c] = 0.0;
+      for (int j = 0; j < n1; ++j) {
+        const double cj = sCt[j * d + r];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) acc[c] = fma(cj, xq[((NX + c) << shift) + j], acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < NU; ++c) A.g[A.gmU + (int64_t)c * (A.N - 1) + s0q + r] = acc[c];
+    }
+
+    // ---- stream the unit's CSR value blocks out: per state / path row they are contiguous
+    if (JAC) {
+      __syncwarp();
+#pragma unroll
+      for (int s = 0; s < NX; ++s)
+        mpx_warp_copy_out(A.vals + A.vF[s] + S0.rowpre * PH::f_next(s) + S0.dpre,
+                          stage + mpx2_region<PH>(rows_cap, n1, s, 0), rows_total * (n1 + PH::f_next(s)), lane);
+#pragma unroll
+      for (int qc = 0; qc < NC; ++qc)
+        mpx_warp_copy_out(A.vals + A.vC[qc] + S0.rowpre * PH::c_len(qc), stage + mpx2_region<PH>(rows_cap, n1, NX, qc),
+                          rows_total * PH::c_len(qc), lane);
+      if (A.flags & MPX_F_DU) {
+        for (int c = 0; c < NU; ++c)
+          for (int qq = 0; qq < cnt; ++qq) {
+            const int rbq = (has0 && qq == 0) ? 0 : 1;
+            const int rowb = (qq == 0 ? 0 : qq * d + has0);
+            mpx_warp_copy_out(A.vals + A.vDU + (int64_t)c * A.nnzD + S0.dpre + (int64_t)rowb * n1, sD + rbq * n1,
+                              (n1 - rbq) * n1, lane);
+          }
+      }
+      if (A.flags & MPX_F_MU) {
+        const double* sC = tab + MpxTab::off_C(n1);
+        for (int c = 0; c < NU; ++c)
+          for (int qq = 0; qq < cnt; ++qq)
+            mpx_warp_copy_out(A.vals + A.vmU + (int64_t)c * A.nnzI + S0.ipre + (int64_t)qq * d * n1, sC, d * n1, lane);
+      }
+      __syncwarp();
     }
   }
 }

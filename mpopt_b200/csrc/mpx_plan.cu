@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -187,7 +188,9 @@ struct mpx_plan {
   // device
   cudaStream_t stream = nullptr;
   DevBuf d_tabs, d_seg_tab, d_seg_start, d_seg_dpre, d_seg_ipre, d_seg_spre, d_z, d_p, d_sig0, d_g, d_vals, d_full,
-      d_grad, d_partial, d_f, d_gather, d_evcols;
+      d_grad, d_partial, d_f, d_gather, d_evcols, d_unit_k, d_unit_n;
+  // v2 (persistent-warp) launch geometry; v2_warps == 0 -> v1 kernel (one CTA per segment)
+  int v2_warps = 0, v2_grid = 0, v2_units = 0, v2_stage_cap = 0, v2_smem_jac = 0, v2_smem_g = 0;
   std::vector<double> h_p_cache;
   bool p_valid = false;
   const MpxProgramEntry* prog = nullptr;
@@ -195,6 +198,7 @@ struct mpx_plan {
   std::vector<MpxPhaseArgs> args;
   int64_t launches = 0;
   int smem_gjac = 0, smem_g = 0, smem_fgrad = 0;
+  bool smem_too_big = false;
   ~mpx_plan() {
     if (stream) cudaStreamDestroy(stream);
   }
@@ -631,9 +635,63 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     p.smem_g = base * 8;
     p.smem_gjac = (base + MpxTab::pad2(stage)) * 8;
     p.smem_fgrad = (MpxTab::size(n1) + MpxTab::pad2((nx + nu) * n1) + 4 * MPX_NPART + 2) * 8;
-    if (p.smem_gjac > 227 * 1024)
-      return fail(MPX_ELIMIT, "segment too large for the shared-memory staged kernel (degree x states)");
+    p.smem_too_big = p.smem_gjac > 227 * 1024;
   }
+
+  // ---- v2 work units: runs of adjacent equal-degree segments, at most 32/pow2ceil(d+1) per unit
+  {
+    const char* force = getenv("MPX_KERNEL");
+    const bool want_v2 = !(force && strcmp(force, "v1") == 0);
+    auto lw_of = [](int dg) { int lw = 2; while (lw < dg + 1) lw <<= 1; return lw; };
+    int stage_cap = 0;
+    for (int dg : p.degs) {
+      const int n1 = dg + 1, rows_cap = (32 / std::max(lw_of(dg), 1)) * dg + 1;
+      for (int ph = 0; ph < p.P && dg <= 31; ++ph) {
+        int s_ = 0;
+        for (int s = 0; s < nx; ++s) s_ += rows_cap * (n1 + p.ph[ph].f_next[s]);
+        for (int c = 0; c < p.ph[ph].nc; ++c) s_ += rows_cap * p.ph[ph].c_len[c];
+        stage_cap = std::max(stage_cap, s_);
+      }
+    }
+    stage_cap = MpxTab::pad2(stage_cap);
+    const long avail = 227L * 1024 - (long)(p.tab_doubles + 2) * 8;
+    const long per_warp = (long)(32 * (nx + nu) + stage_cap) * 8;
+    int warps = (int)std::min<long>(MPX2_MAX_THREADS / 32, avail > 0 ? avail / per_warp : 0);
+    if (want_v2 && dmax <= 31 && warps >= 1 && p.tab_doubles * 8L <= 96L * 1024) {
+      std::vector<int32_t> uk, un;
+      for (int k = p.seg_begin; k < p.seg_end;) {
+        const int dg = p.po[k], cap = 32 / lw_of(dg);
+        int n = 1;
+        while (n < cap && k + n < p.seg_end && p.po[k + n] == dg) ++n;
+        uk.push_back(k), un.push_back(n);
+        k += n;
+      }
+      if (!p.uniform) {  // heavier units first so the static round-robin over warps stays balanced
+        std::vector<int> idx(uk.size());
+        for (size_t i = 0; i < idx.size(); ++i) idx[i] = (int)i;
+        std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) {
+          return (long)un[a] * p.po[uk[a]] * (p.po[uk[a]] + 1) > (long)un[b] * p.po[uk[b]] * (p.po[uk[b]] + 1);
+        });
+        std::vector<int32_t> k2, n2;
+        for (int i : idx) k2.push_back(uk[i]), n2.push_back(un[i]);
+        uk.swap(k2), un.swap(n2);
+      }
+      cudaDeviceProp prop;
+      CUDA_TRY(cudaGetDeviceProperties(&prop, p.device));
+      p.v2_units = (int)uk.size();
+      p.v2_warps = std::max(1, std::min(warps, (p.v2_units + prop.multiProcessorCount - 1) / prop.multiProcessorCount));
+      p.v2_grid = std::min(prop.multiProcessorCount, (p.v2_units + p.v2_warps - 1) / p.v2_warps);
+      p.v2_stage_cap = stage_cap;
+      p.v2_smem_jac = (int)((p.tab_doubles + 2) * 8 + p.v2_warps * per_warp);
+      p.v2_smem_g = (int)((p.tab_doubles + 2) * 8 + p.v2_warps * (long)(32 * (nx + nu)) * 8);
+      CUDA_TRY(up(p.d_unit_k, uk.data(), uk.size() * sizeof(int32_t)));
+      CUDA_TRY(up(p.d_unit_n, un.data(), un.size() * sizeof(int32_t)));
+    }
+  }
+
+  if (p.v2_warps == 0 && p.smem_too_big)
+    return fail(MPX_ELIMIT, "segment too large for the shared-memory staged kernels (degree x states)");
+  p.origin += p.v2_warps > 0 ? ";gjac=v2" : ";gjac=v1";
 
   // ---- kernel arguments per phase (pointers filled per call)
   p.args.resize(p.P);
@@ -648,6 +706,8 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     a.seg_ipre = p.d_seg_ipre.as<int64_t>();
     a.K = K, a.N = N, a.seg_begin = p.seg_begin, a.seg_end = p.seg_end;
     a.uniform_deg = p.uniform ? p.po[0] : 0;
+    a.unit_k = p.d_unit_k.as<int32_t>(), a.unit_n = p.d_unit_n.as<int32_t>();
+    a.n_units = p.v2_units, a.tab_doubles = p.tab_doubles, a.stage_cap = p.v2_stage_cap;
     a.flags = (L.has_DU ? MPX_F_DU : 0) | (L.has_mU ? MPX_F_MU : 0) | (p.seg_end == K ? MPX_F_TAIL : 0);
     a.accumulate_f = ph > 0;
     a.zoff = L.zoff;
@@ -789,7 +849,10 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     MpxPhaseArgs& a = p.args[ph];
     a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
     a.g = d_g, a.vals = target;
-    CUDA_TRY(p.prog->phases[ph]->gjac(a, jac, grid, jac ? p.smem_gjac : p.smem_g, st));
+    if (p.v2_warps > 0)
+      CUDA_TRY(p.prog->phases[ph]->gjac2(a, jac, p.v2_grid, p.v2_warps * 32, jac ? p.v2_smem_jac : p.v2_smem_g, st));
+    else
+      CUDA_TRY(p.prog->phases[ph]->gjac(a, jac, grid, jac ? p.smem_gjac : p.smem_g, st));
     ++p.launches;
     const PhaseLayout& L = p.ph[ph];
     if (L.has_dU) {

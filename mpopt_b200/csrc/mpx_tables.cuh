@@ -166,11 +166,14 @@ __global__ void __launch_bounds__(MPX_TAB_THREADS) mpx_tables_kernel(int scheme,
         if (m != i && m != j) v *= (R[i] - R[m]) / (R[j] - R[m]);
     }
     D[e] = v;
+    rec[MpxTab::off_Dt(n1) + j * n1 + i] = v;
   }
   double* C = rec + MpxTab::off_C(n1);
   for (int e = threadIdx.x; e < d * n1; e += blockDim.x) {
     const int m = e / n1, j = e - m * n1;
-    C[e] = mpx_lagrange(R, n1, j, (R[m] + R[m + 1]) / 2.0);  // mpopt.py:350-352
+    const double v = mpx_lagrange(R, n1, j, (R[m] + R[m + 1]) / 2.0);  // mpopt.py:350-352
+    C[e] = v;
+    rec[MpxTab::off_Ct(n1) + j * d + m] = v;
   }
 }
 

@@ -14,6 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from .layout import Layout
 from .program import Program
 
 
@@ -56,6 +57,8 @@ class Transcription:
             d.diff_u, d.midu = int(bool(o.diff_u[ph])), int(mid)
             d.du_continuity = int(bool(o.du_continuity[ph]))
             d.cost_t = int(not pp.Lt.is_value(0.0))
+        self.layout = Layout(self.program, self.poly_orders, [bool(v) for v in o.diff_u], self.has_mU,
+                             [bool(v) for v in o.du_continuity], len(o.phase_links) if self.P > 1 else 0)
         po = np.asarray(self.poly_orders, dtype=np.int32)
         sx, su, sa = (np.ascontiguousarray(np.asarray(v, dtype=float)) for v in (o.scale_x, o.scale_u, o.scale_a))
         links = np.asarray(o.phase_links if self.P > 1 else [], dtype=np.int32).reshape(-1)

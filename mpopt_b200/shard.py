@@ -1,0 +1,150 @@
+"""Segment sharding over GPUs and the per-evaluation all-gather of the shards' g / Jacobian blocks.
+
+The reference has no parallelism of any kind; the axis the *problem* offers is that, given the replicated
+decision vector, every row owned by a segment is independent.  Rank r evaluates the
+contiguous segment range ``partition(...)[r]`` with the same kernels, writing its rows straight into a
+full-size ``g`` / ``values`` buffer at their final CSR positions; because rows are state-major, a shard's
+output is a handful of contiguous runs (``Layout.shard_runs``), not one block.
+
+``Gatherer`` makes every rank's buffers complete with ONE collective per evaluation:
+
+* ``inplace``  (uniform degrees, K divisible by the world size): the runs of all ranks tile each block with
+  equal sizes once rank 0's extra first row (global node 0) is set aside, so each block is an in-place
+  ``all_gather_into_tensor`` on a view of the final buffer; the calls are coalesced into one NCCL group.
+  Row 0 is recomputed locally by every rank (a one-segment plan), which is cheaper than broadcasting it.
+* ``packed``   (anything else): runs are packed into one send buffer, gathered, and scattered back.
+
+Works with any ``torch.distributed`` backend (NCCL on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def partition(poly_orders, world):
+    """Contiguous segment ranges [(begin, end)] * world, balanced by the Jacobian work p(p+1) per segment."""
+    po = np.asarray(poly_orders, dtype=np.int64)
+    K = len(po)
+    if world > K:
+        raise ValueError("more ranks than segments")
+    if len(set(po.tolist())) == 1 and K % world == 0:
+        step = K // world
+        return [(r * step, (r + 1) * step) for r in range(world)]
+    cost = np.cumsum(po * (po + 1), dtype=np.float64)
+    cuts = [0]
+    for r in range(1, world):
+        k = int(np.searchsorted(cost, cost[-1] * r / world)) + 1
+        k = min(max(k, cuts[-1] + 1), K - (world - r))
+        cuts.append(k)
+    cuts.append(K)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class GatherPlan:
+    """Pure index logic of the gather (testable without a GPU)."""
+
+    def __init__(self, layout, part):
+        self.world = len(part)
+        self.layout = layout
+        self.runs = {kind: [layout.shard_runs(kind, kb, ke) for kb, ke in part] for kind in (0, 1)}
+        self.mode = "inplace" if self._tiles() else "packed"
+
+    def _tiles(self):
+        layout = self.layout
+        """True if, apart from a leading piece of rank 0, corresponding runs of consecutive ranks are adjacent and
+        of equal size (then each block is an in-place all-gather)."""
+        self.blocks = {0: [], 1: []}  # (kind) -> [(start, count_per_rank)]
+        for kind in (0, 1):
+            rr = self.runs[kind]
+            n_common = min(len(r) for r in rr)
+            # tail-only runs (terminal rows, events) exist on the last rank only: broadcast-free if absent
+            if any(len(r) != n_common for r in rr[:-1]):
+                return False
+            self.extra = getattr(self, "extra", {})
+            self.extra[kind] = rr[-1][n_common:]
+            node0 = layout.node0_counts(kind)
+            if len(node0) < n_common:
+                return False
+            for i in range(n_common):
+                cnt = rr[-1][i][1]
+                if any(r[i][1] != cnt for r in rr[1:]):
+                    return False
+                lead = rr[0][i][1] - cnt
+                if lead != node0[i]:  # rank 0 may only exceed the others by global node 0's row
+                    return False
+                start = rr[0][i][0] + lead
+                for r in range(self.world):
+                    if rr[r][i][0] + (lead if r == 0 else 0) != start + r * cnt:
+                        return False
+                self.blocks[kind].append((start, cnt, rr[0][i][0], lead))
+        return True
+
+
+class Gatherer:
+    def __init__(self, layout, part, dist, rank, device=None, row0_eval=None):
+        """``row0_eval(g, vals)``: evaluates segment 0 locally into the buffers (ranks != 0, inplace mode)."""
+        self.plan = GatherPlan(layout, part)
+        self.dist, self.rank, self.world, self.device = dist, rank, len(part), device
+        self.row0_eval = row0_eval
+        self.mode = self.plan.mode
+        if self.mode == "inplace" and any(self.plan.extra[k] for k in (0, 1)):
+            # terminal / event rows live on the last rank only: tiny, sent with a broadcast
+            self.tail_runs = {k: self.plan.extra[k] for k in (0, 1)}
+        else:
+            self.tail_runs = {0: [], 1: []}
+        self._send = self._recv = None
+
+    # ------------------------------------------------------------------ in-place mode
+    def _inplace(self, g, vals):
+        dist = self.dist
+        if self.rank != 0 and self.row0_eval is not None:
+            self.row0_eval(g, vals)  # global node 0's rows, recomputed locally
+        bufs = {0: g, 1: vals}
+        ops = [(bufs[k][start:start + self.world * cnt], bufs[k][start + self.rank * cnt:start + (self.rank + 1) * cnt])
+               for k in (0, 1) for (start, cnt, _, _) in self.plan.blocks[k]]
+        cm = getattr(dist, "_coalescing_manager", None)
+        if cm is not None and dist.get_backend() == "nccl":
+            with cm(device=self.device):
+                for out, inp in ops:
+                    dist.all_gather_into_tensor(out, inp)
+        else:
+            for out, inp in ops:
+                dist.all_gather_into_tensor(out, inp.clone())
+        for k in (0, 1):
+            for off, cnt in self.tail_runs[k]:
+                dist.broadcast(bufs[k][off:off + cnt], src=self.world - 1)
+
+    # ------------------------------------------------------------------ packed mode
+    def _packed(self, g, vals):
+        import torch
+
+        dist = self.dist
+        runs = self.plan.runs
+        lens = [sum(c for _, c in runs[0][r]) + sum(c for _, c in runs[1][r]) for r in range(self.world)]
+        mx = max(lens)
+        if self._send is None:
+            self._send = torch.empty(mx, dtype=g.dtype, device=g.device)
+            self._recv = torch.empty(mx * self.world, dtype=g.dtype, device=g.device)
+        mine = [g[o:o + c] for o, c in runs[0][self.rank]] + [vals[o:o + c] for o, c in runs[1][self.rank]]
+        torch.cat(mine, out=self._send[:lens[self.rank]])
+        dist.all_gather_into_tensor(self._recv, self._send)
+        dst, src = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            pos = r * mx
+            for buf, kind in ((g, 0), (vals, 1)):
+                for o, c in runs[kind][r]:
+                    dst.append(buf[o:o + c])
+                    src.append(self._recv[pos:pos + c])
+                    pos += c
+        torch._foreach_copy_(dst, src)
+
+    def all_gather(self, g, vals):
+        """Complete ``g`` and ``vals`` (full-size tensors holding this rank's shard) on every rank."""
+        if self.world == 1:
+            return
+        if self.mode == "inplace":
+            self._inplace(g, vals)
+        else:
+            self._packed(g, vals)

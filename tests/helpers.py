@@ -26,3 +26,27 @@ def random_point(oracle, seed=20261017, tf=None, dirichlet=False):
     else:
         p = oracle.seg_width_params()
     return z, p
+
+
+def eval_expr(outputs, env):
+    """Numerically evaluate traced expressions (mpopt_b200.trace.Expr) at a point: test-only interpreter."""
+    import math
+
+    from mpopt_b200 import trace as tr
+
+    val = {}
+    fun = {"neg": lambda a: -a, "sqrt": math.sqrt, "exp": math.exp, "log": math.log, "sin": math.sin, "cos": math.cos,
+           "tan": math.tan, "asin": math.asin, "acos": math.acos, "atan": math.atan, "sinh": math.sinh,
+           "cosh": math.cosh, "tanh": math.tanh, "fabs": abs, "sign": lambda a: (a > 0) - (a < 0), "sq": lambda a: a * a}
+    for e in tr.topo([tr.as_expr(o) for o in outputs]):
+        if e.op == "const":
+            val[e.id] = e.value
+        elif e.op == "var":
+            val[e.id] = env[e.name]
+        elif e.op in ("add", "sub", "mul", "div", "pow"):
+            a, b = (val[x.id] for x in e.args)
+            val[e.id] = {"add": a + b, "sub": a - b, "mul": a * b, "div": a / b if e.op == "div" else 0.0,
+                         "pow": a ** b if e.op == "pow" else 0.0}[e.op]
+        else:
+            val[e.id] = fun[e.op](val[e.args[0].id])
+    return [val[tr.as_expr(o).id] for o in outputs]
