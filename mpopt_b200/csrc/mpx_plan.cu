@@ -191,6 +191,9 @@ struct mpx_plan {
       d_grad, d_partial, d_f, d_gather, d_evcols, d_unit_k, d_unit_n;
   // v2 (persistent-warp) launch geometry; v2_warps == 0 -> v1 kernel (one CTA per segment)
   int v2_warps = 0, v2_grid = 0, v2_units = 0, v2_stage_cap = 0, v2_smem_jac = 0, v2_smem_g = 0;
+  // v3 (row-block warps): per-phase grid, shared scratch per warp
+  int v3 = 0, num_sms = 0;
+  std::vector<int> v3_grid, v3_threads, v3_smem, v3_smem_g, v3_stage;
   std::vector<double> h_p_cache;
   bool p_valid = false;
   const MpxProgramEntry* prog = nullptr;
@@ -642,21 +645,21 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   {
     const char* force = getenv("MPX_KERNEL");
     const bool want_v2 = !(force && strcmp(force, "v1") == 0);
+    const bool want_v3 = force && strcmp(force, "v3") == 0;  // row-block teams: kept for comparison, slower than v2
     auto lw_of = [](int dg) { int lw = 2; while (lw < dg + 1) lw <<= 1; return lw; };
-    int stage_cap = 0;
+    int stage_cap = 0;  // widest single row-block image over degrees / phases
     for (int dg : p.degs) {
       const int n1 = dg + 1, rows_cap = (32 / std::max(lw_of(dg), 1)) * dg + 1;
       for (int ph = 0; ph < p.P && dg <= 31; ++ph) {
-        int s_ = 0;
-        for (int s = 0; s < nx; ++s) s_ += rows_cap * (n1 + p.ph[ph].f_next[s]);
-        for (int c = 0; c < p.ph[ph].nc; ++c) s_ += rows_cap * p.ph[ph].c_len[c];
-        stage_cap = std::max(stage_cap, s_);
+        for (int s = 0; s < nx; ++s) stage_cap = std::max(stage_cap, rows_cap * (n1 + p.ph[ph].f_next[s]));
+        for (int c = 0; c < p.ph[ph].nc; ++c) stage_cap = std::max(stage_cap, rows_cap * p.ph[ph].c_len[c]);
       }
     }
     stage_cap = MpxTab::pad2(stage_cap);
     const long avail = 227L * 1024 - (long)(p.tab_doubles + 2) * 8;
     const long per_warp = (long)(32 * (nx + nu) + stage_cap) * 8;
     int warps = (int)std::min<long>(MPX2_MAX_THREADS / 32, avail > 0 ? avail / per_warp : 0);
+    if (const char* wenv = getenv("MPX_V2_WARPS")) warps = std::max(1, std::min(warps, atoi(wenv)));
     if (want_v2 && dmax <= 31 && warps >= 1 && p.tab_doubles * 8L <= 96L * 1024) {
       std::vector<int32_t> uk, un;
       for (int k = p.seg_begin; k < p.seg_end;) {
@@ -676,8 +679,36 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
         for (int i : idx) k2.push_back(uk[i]), n2.push_back(un[i]);
         uk.swap(k2), un.swap(n2);
       }
-      cudaDeviceProp prop;
-      CUDA_TRY(cudaGetDeviceProperties(&prop, p.device));
+      int nsm = 0;
+      CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
+      p.num_sms = nsm;
+      struct { int multiProcessorCount; } prop{nsm};
+      // v3: CTA = T teams of RT = nx + nc warps; per warp 32 doubles of node values + the image of its row block
+      p.v3_threads.assign(p.P, 0), p.v3_grid.assign(p.P, 0), p.v3_smem.assign(p.P, 0), p.v3_smem_g.assign(p.P, 0);
+      p.v3_stage.assign(p.P, 0);
+      bool ok3 = want_v3;
+      for (int ph = 0; ph < p.P && ok3; ++ph) {
+        const int RT = nx + p.ph[ph].nc;
+        int img = 0;  // widest row-block image over degrees
+        for (int dg : p.degs) {
+          const int n1 = dg + 1, rows_cap = (32 / lw_of(dg)) * dg + 1;
+          for (int s = 0; s < nx; ++s) img = std::max(img, rows_cap * (n1 + p.ph[ph].f_next[s]));
+          for (int c = 0; c < p.ph[ph].nc; ++c) img = std::max(img, rows_cap * p.ph[ph].c_len[c]);
+        }
+        img = MpxTab::pad2(img);
+        if (RT < 1 || RT > MPX3_MAX_THREADS / 32) { ok3 = false; break; }
+        const int T = std::max(1, std::min(8 / RT, (int)((uk.size() + p.num_sms - 1) / p.num_sms)));
+        const int warps = RT * T;
+        const long smem = (long)(p.tab_doubles + 2 + (long)warps * (32 + img)) * 8;
+        if (smem > 227L * 1024) { ok3 = false; break; }
+        // resident CTAs per SM: shared memory, and ~20 warps (96 registers per thread)
+        const int per_sm = (int)std::max<long>(1, std::min<long>(std::min<long>(227L * 1024 / (smem + 1024), std::max(1, 20 / warps)), 8));
+        p.v3_threads[ph] = warps * 32, p.v3_stage[ph] = img;
+        p.v3_smem[ph] = (int)smem;
+        p.v3_smem_g[ph] = (int)((p.tab_doubles + 2 + (long)warps * 32) * 8);
+        p.v3_grid[ph] = (int)std::max<long>(1, std::min<long>((long)per_sm * p.num_sms, ((long)uk.size() + T - 1) / T));
+      }
+      p.v3 = ok3 ? 1 : 0;
       p.v2_units = (int)uk.size();
       p.v2_warps = std::max(1, std::min(warps, (p.v2_units + prop.multiProcessorCount - 1) / prop.multiProcessorCount));
       p.v2_grid = std::min(prop.multiProcessorCount, (p.v2_units + p.v2_warps - 1) / p.v2_warps);
@@ -691,7 +722,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
 
   if (p.v2_warps == 0 && p.smem_too_big)
     return fail(MPX_ELIMIT, "segment too large for the shared-memory staged kernels (degree x states)");
-  p.origin += p.v2_warps > 0 ? ";gjac=v2" : ";gjac=v1";
+  p.origin += p.v3 ? ";gjac=v3" : (p.v2_warps > 0 ? ";gjac=v2" : ";gjac=v1");
 
   // ---- kernel arguments per phase (pointers filled per call)
   p.args.resize(p.P);
@@ -709,6 +740,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     a.unit_k = p.d_unit_k.as<int32_t>(), a.unit_n = p.d_unit_n.as<int32_t>();
     a.n_units = p.v2_units, a.tab_doubles = p.tab_doubles, a.stage_cap = p.v2_stage_cap;
     a.flags = (L.has_DU ? MPX_F_DU : 0) | (L.has_mU ? MPX_F_MU : 0) | (p.seg_end == K ? MPX_F_TAIL : 0);
+    if (const char* dbg = getenv("MPX_DEBUG_FLAGS")) a.flags |= atoi(dbg) & (MPX_F_DBG_NOSTORE | MPX_F_DBG_STOREONLY);
     a.accumulate_f = ph > 0;
     a.zoff = L.zoff;
     a.gF = L.gF, a.gC = L.gC, a.gDU = L.gDU, a.gmU = L.gmU, a.gTC = L.gTC;
@@ -720,6 +752,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     for (int c = 0; c < nu; ++c) a.isu[c] = 1.0 / p.su[c];
     for (int m = 0; m < na; ++m) a.isa[m] = 1.0 / p.sa[m];
     a.st = p.st, a.delta = p.tau_max - p.tau_min, a.tau0 = p.tau_min;
+    a.ist = 1.0 / a.st, a.idelta = 1.0 / a.delta;
   }
   *out = pp.release();
   return MPX_OK;
@@ -849,7 +882,10 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     MpxPhaseArgs& a = p.args[ph];
     a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
     a.g = d_g, a.vals = target;
-    if (p.v2_warps > 0)
+    if (p.v3) {
+      a.stage_cap = p.v3_stage[ph];
+      CUDA_TRY(p.prog->phases[ph]->gjac3(a, jac, p.v3_grid[ph], p.v3_threads[ph], jac ? p.v3_smem[ph] : p.v3_smem_g[ph], st));
+    } else if (p.v2_warps > 0)
       CUDA_TRY(p.prog->phases[ph]->gjac2(a, jac, p.v2_grid, p.v2_warps * 32, jac ? p.v2_smem_jac : p.v2_smem_g, st));
     else
       CUDA_TRY(p.prog->phases[ph]->gjac(a, jac, grid, jac ? p.smem_gjac : p.smem_g, st));

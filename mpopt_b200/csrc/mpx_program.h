@@ -15,6 +15,8 @@ struct MpxPhaseKernels {
   virtual cudaError_t gjac(const MpxPhaseArgs& a, bool jac, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem,
                             cudaStream_t st) const = 0;
+  virtual cudaError_t gjac3(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem,
+                            cudaStream_t st) const = 0;
   virtual cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const = 0;
 };
@@ -63,6 +65,19 @@ struct MpxAotPhase final : MpxPhaseKernels {
     } else {
       if ((e = allow_smem(mpx_gjac2_kernel<PH, false>, smem, d0)) != cudaSuccess) return e;
       mpx_gjac2_kernel<PH, false><<<grid, threads, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+  }
+  cudaError_t gjac3(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem,
+                    cudaStream_t st) const override {
+    static bool d0 = false, d1 = false;
+    cudaError_t e;
+    if (jac) {
+      if ((e = allow_smem(mpx_gjac3_kernel<PH, true>, smem, d1)) != cudaSuccess) return e;
+      mpx_gjac3_kernel<PH, true><<<grid, threads, smem, st>>>(a);
+    } else {
+      if ((e = allow_smem(mpx_gjac3_kernel<PH, false>, smem, d0)) != cudaSuccess) return e;
+      mpx_gjac3_kernel<PH, false><<<grid, threads, smem, st>>>(a);
     }
     return cudaGetLastError();
   }

@@ -190,6 +190,10 @@ class PhaseProgram:
         L.append(self._switch("f_next", next_, 0))
         L.append(self._switch("f_tpos", tpos))
         L.append(self._switch("f_diag", diag))
+        first = lambda rows, n: [next((e for e, r in enumerate(rows) if r == k), 0) for k in range(n)]
+        count = lambda rows, n: [sum(1 for r in rows if r == k) for k in range(n)]
+        L.append(self._switch("jf_first", first(jf_row, nx), 0))
+        L.append(self._switch("jf_count", count(jf_row, nx), 0))
         L.append(self._switch("jf_row", jf_row))
         L.append(self._switch("jf_pos", jf_pos))
         L.append(self._switch("jf_var", jf_var))
@@ -207,6 +211,8 @@ class PhaseProgram:
             jc_row.append(r), jc_var.append(v), jc_pos.append(cpos[(r, kind)])
         L.append(self._switch("c_len", c_len, 0))
         L.append(self._switch("c_tpos", c_tpos))
+        L.append(self._switch("jc_first", first(jc_row, nc), 0))
+        L.append(self._switch("jc_count", count(jc_row, nc), 0))
         L.append(self._switch("jc_row", jc_row))
         L.append(self._switch("jc_pos", jc_pos))
         L.append(self._switch("jc_var", jc_var))
@@ -239,10 +245,24 @@ class PhaseProgram:
         tg = [f"f[{s}]" for s in range(nx)] + [f"jf[{e}]" for e in range(len(self.jf))] + [f"ft[{s}]" for s in range(nx)]
         L += fn(f"dyn({node_sig}, double* __restrict__ f, double* __restrict__ jf, double* __restrict__ ft)", outs, tg,
                 self._var_ref(), "d")
+        # one function per row: the row-block kernels evaluate only the row they assemble; jr[] holds the row's
+        # packed partials (entries jf_first(s) .. jf_first(s)+jf_count(s)-1 of the full list)
+        for s in range(nx):
+            ent = [d for (r, _, d) in self.jf if r == s]
+            outs = [self.f[s]] + ent + [self.ft[s]]
+            tg = ["f[0]"] + [f"jr[{i}]" for i in range(len(ent))] + ["f[1]"]
+            L += fn(f"dyn_row(mpx_int<{s}>, {node_sig}, double* __restrict__ f, double* __restrict__ jr)", outs, tg,
+                    self._var_ref(), "d")
         outs = self.c + [d for _, _, d in self.jc] + self.ct
         tg = [f"c[{q}]" for q in range(nc)] + [f"jc[{e}]" for e in range(len(self.jc))] + [f"ct[{q}]" for q in range(nc)]
         L += fn(f"path({node_sig}, double* __restrict__ c, double* __restrict__ jc, double* __restrict__ ct)", outs, tg,
                 self._var_ref(), "c")
+        for q in range(nc):
+            ent = [d for (r, _, d) in self.jc if r == q]
+            outs = [self.c[q]] + ent + [self.ct[q]]
+            tg = ["c[0]"] + [f"jr[{i}]" for i in range(len(ent))] + ["c[1]"]
+            L += fn(f"path_row(mpx_int<{q}>, {node_sig}, double* __restrict__ c, double* __restrict__ jr)", outs, tg,
+                    self._var_ref(), "c")
         outs = [self.L] + [d for _, d in self.gL] + [self.Lt]
         tg = ["L[0]"] + [f"gl[{e}]" for e in range(len(self.gL))] + ["L[1]"]
         L += fn(f"cost({node_sig}, double* __restrict__ L, double* __restrict__ gl)", outs, tg, self._var_ref(), "q")
