@@ -292,7 +292,7 @@ def run_cuda(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
-    cb = cpu_baseline(budget_s=args.cpu_budget, cores=1) if not args.no_cpu else None
+    cb = cpu_baseline(budget_s=args.cpu_budget, cores=1) if (not args.no_cpu and world == 1) else None
     line = {
         "metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",

@@ -285,6 +285,192 @@ extern "C" int mpx_collocation_weights(int32_t scheme, int32_t deg, double tau_m
   return MPX_OK;
 }
 
+
+// ------------------------------------------------------------------ run-time compiled programs (NVRTC)
+// Problems whose generated functors were not compiled ahead of time are compiled here from the SAME kernel header
+// (csrc/mpx_kernels.cuh, read from disk next to libmpx.so) plus the generated source handed over the C ABI.
+// libnvrtc and libcuda are opened lazily so that libmpx.so itself loads on machines without a driver.
+namespace {
+typedef int nvrtcResult_t;
+typedef struct _nvrtcProgram* nvrtcProgram_t;
+typedef int CUresult_t;
+typedef struct CUmod_st* CUmodule_t;
+typedef struct CUfunc_st* CUfunction_t;
+
+struct RtApi {
+  bool ok = false;
+  std::string err;
+  nvrtcResult_t (*CreateProgram)(nvrtcProgram_t*, const char*, const char*, int, const char* const*, const char* const*);
+  nvrtcResult_t (*AddNameExpression)(nvrtcProgram_t, const char*);
+  nvrtcResult_t (*CompileProgram)(nvrtcProgram_t, int, const char* const*);
+  nvrtcResult_t (*GetProgramLogSize)(nvrtcProgram_t, size_t*);
+  nvrtcResult_t (*GetProgramLog)(nvrtcProgram_t, char*);
+  nvrtcResult_t (*GetCUBINSize)(nvrtcProgram_t, size_t*);
+  nvrtcResult_t (*GetCUBIN)(nvrtcProgram_t, char*);
+  nvrtcResult_t (*GetLoweredName)(nvrtcProgram_t, const char*, const char**);
+  nvrtcResult_t (*DestroyProgram)(nvrtcProgram_t*);
+  CUresult_t (*ModuleLoadData)(CUmodule_t*, const void*);
+  CUresult_t (*ModuleGetFunction)(CUfunction_t*, CUmodule_t, const char*);
+  CUresult_t (*FuncSetAttribute)(CUfunction_t, int, int);
+  CUresult_t (*LaunchKernel)(CUfunction_t, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*,
+                             void**, void**);
+};
+
+template <class F>
+bool load_sym(void* h, const char* name, F& f, std::string& err) {
+  f = reinterpret_cast<F>(dlsym(h, name));
+  if (!f) err = std::string("missing symbol ") + name;
+  return f != nullptr;
+}
+
+RtApi& rt_api() {
+  static RtApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* hn = nullptr;
+  for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"})
+    if ((hn = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!hn || !hc) {
+    api.err = !hn ? "libnvrtc.so.12 not found" : "libcuda.so.1 not found";
+    return api;
+  }
+  api.ok = load_sym(hn, "nvrtcCreateProgram", api.CreateProgram, api.err) &&
+           load_sym(hn, "nvrtcAddNameExpression", api.AddNameExpression, api.err) &&
+           load_sym(hn, "nvrtcCompileProgram", api.CompileProgram, api.err) &&
+           load_sym(hn, "nvrtcGetProgramLogSize", api.GetProgramLogSize, api.err) &&
+           load_sym(hn, "nvrtcGetProgramLog", api.GetProgramLog, api.err) &&
+           load_sym(hn, "nvrtcGetCUBINSize", api.GetCUBINSize, api.err) &&
+           load_sym(hn, "nvrtcGetCUBIN", api.GetCUBIN, api.err) &&
+           load_sym(hn, "nvrtcGetLoweredName", api.GetLoweredName, api.err) &&
+           load_sym(hn, "nvrtcDestroyProgram", api.DestroyProgram, api.err) &&
+           load_sym(hc, "cuModuleLoadData", api.ModuleLoadData, api.err) &&
+           load_sym(hc, "cuModuleGetFunction", api.ModuleGetFunction, api.err) &&
+           load_sym(hc, "cuFuncSetAttribute", api.FuncSetAttribute, api.err) &&
+           load_sym(hc, "cuLaunchKernel", api.LaunchKernel, api.err);
+  return api;
+}
+
+// launches through the driver API; same interface as the AOT phases
+struct MpxRtPhase final : MpxPhaseKernels {
+  CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_fgrad[2] = {nullptr, nullptr},
+               f_final[2] = {nullptr, nullptr};
+  static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+    RtApi& R = rt_api();
+    if (smem > 48 * 1024 && R.FuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, 227 * 1024) != 0)
+      return cudaErrorInvalidValue;
+    void* params[] = {const_cast<MpxPhaseArgs*>(&a)};
+    return R.LaunchKernel(f, grid, 1, 1, threads, 1, 1, (unsigned)smem, st, params, nullptr) == 0 ? cudaSuccess
+                                                                                                : cudaErrorLaunchFailure;
+  }
+  cudaError_t gjac(const MpxPhaseArgs& a, bool jac, int grid, size_t smem, cudaStream_t st) const override {
+    return go(f_gjac[jac], a, grid, MPX_THREADS, smem, st);
+  }
+  cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) const override {
+    return go(f_gjac2[jac], a, grid, threads, smem, st);
+  }
+  cudaError_t gjac3(const MpxPhaseArgs&, bool, int, int, size_t, cudaStream_t) const override {
+    return cudaErrorNotSupported;
+  }
+  cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const override {
+    return go(f_fgrad[grad], a, grid, MPX_THREADS, smem, st);
+  }
+  cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const override {
+    return go(f_final[grad], a, 1, 256, 0, st);
+  }
+};
+
+struct RtProgram {
+  std::string key;
+  std::vector<std::unique_ptr<MpxRtPhase>> phases;
+  std::vector<const MpxPhaseKernels*> ptrs;
+  MpxProgramEntry entry;
+};
+std::vector<std::unique_ptr<RtProgram>> g_rt_programs;  // kept for the life of the process (modules stay loaded)
+
+std::string lib_dir() {
+  Dl_info info;
+  if (dladdr(reinterpret_cast<void*>(&mpx_version), &info) && info.dli_fname) {
+    std::string p(info.dli_fname);
+    size_t k = p.rfind('/');
+    return k == std::string::npos ? "." : p.substr(0, k);
+  }
+  return ".";
+}
+
+int compile_program(const char* key, const char* source, int n_phases, const MpxProgramEntry** out) {
+  RtApi& R = rt_api();
+  if (!R.ok) return fail(MPX_ENOPROGRAM, "program '" + std::string(key) + "' is not compiled in and NVRTC is unavailable: " + R.err);
+  const std::string hdr_path = lib_dir() + "/csrc/mpx_kernels.cuh";
+  FILE* fh = fopen(hdr_path.c_str(), "rb");
+  if (!fh) return fail(MPX_ENOPROGRAM, "cannot read " + hdr_path + " for run-time compilation");
+  std::string hdr;
+  char buf[65536];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, fh)) > 0) hdr.append(buf, n);
+  fclose(fh);
+  std::string src = hdr + "\n#define MPX_PHASE_NAME(k) MpxPhRt_##k\n" + source + "\n";
+  nvrtcProgram_t prog = nullptr;
+  if (R.CreateProgram(&prog, src.c_str(), "mpx_rt.cu", 0, nullptr, nullptr) != 0) return fail(MPX_ECUDA, "nvrtcCreateProgram failed");
+  std::vector<std::string> names;
+  for (int ph = 0; ph < n_phases; ++ph)
+    for (const char* k : {"mpx_gjac_kernel", "mpx_gjac2_kernel", "mpx_fgrad_kernel", "mpx_fgrad_final"})
+      for (const char* b : {"false", "true"})
+        names.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ", " + b + ">");
+  for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  const nvrtcResult_t rc = R.CompileProgram(prog, 3, opts);
+  if (rc != 0) {
+    size_t ls = 0;
+    R.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls) R.GetProgramLog(prog, &log[0]);
+    R.DestroyProgram(&prog);
+    return fail(MPX_ECUDA, "NVRTC compilation of the node functors failed:\n" + log.substr(0, 4000));
+  }
+  size_t cs = 0;
+  R.GetCUBINSize(prog, &cs);
+  std::vector<char> cubin(cs);
+  R.GetCUBIN(prog, cubin.data());
+  cudaFree(0);  // make sure the primary context is current for the driver calls below
+  CUmodule_t mod = nullptr;
+  if (R.ModuleLoadData(&mod, cubin.data()) != 0) {
+    R.DestroyProgram(&prog);
+    return fail(MPX_ECUDA, "cuModuleLoadData failed for the run-time compiled program");
+  }
+  std::unique_ptr<RtProgram> rp(new RtProgram());
+  rp->key = key;
+  size_t idx = 0;
+  for (int ph = 0; ph < n_phases; ++ph) {
+    std::unique_ptr<MpxRtPhase> P(new MpxRtPhase());
+    CUfunction_t* slots[4] = {P->f_gjac, P->f_gjac2, P->f_fgrad, P->f_final};
+    for (int k = 0; k < 4; ++k)
+      for (int b = 0; b < 2; ++b, ++idx) {
+        const char* lowered = nullptr;
+        if (R.GetLoweredName(prog, names[idx].c_str(), &lowered) != 0 || !lowered ||
+            R.ModuleGetFunction(&slots[k][b], mod, lowered) != 0) {
+          R.DestroyProgram(&prog);
+          return fail(MPX_ECUDA, "kernel " + names[idx] + " not found in the run-time compiled module");
+        }
+      }
+    rp->ptrs.push_back(P.get());
+    rp->phases.push_back(std::move(P));
+  }
+  R.DestroyProgram(&prog);
+  rp->entry = MpxProgramEntry{rp->key.c_str(), n_phases, rp->ptrs.data(), nullptr};
+  *out = &rp->entry;
+  g_rt_programs.push_back(std::move(rp));
+  return MPX_OK;
+}
+
+const MpxProgramEntry* find_rt_program(const char* key) {
+  for (auto& rp : g_rt_programs)
+    if (rp->key == key) return &rp->entry;
+  return nullptr;
+}
+}  // namespace
+
 // ------------------------------------------------------------------ structure
 namespace {
 struct Builder {
@@ -502,11 +688,22 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
 
   // ---- program
   p.prog = mpx_find_program(d->program_key);
-  if (!p.prog)
-    return fail(MPX_ENOPROGRAM, std::string("no compiled node functors registered for program key '") +
-                                    (d->program_key ? d->program_key : "(null)") + "'");
+  p.origin = "aot:";
+  if (!p.prog && d->program_key) {
+    p.origin = "nvrtc:";
+    p.prog = find_rt_program(d->program_key);
+    if (!p.prog) {
+      if (!d->program_source)
+        return fail(MPX_ENOPROGRAM, std::string("no compiled node functors registered for program key '") +
+                                        d->program_key + "' and no program_source given");
+      int rc_ = compile_program(d->program_key, d->program_source, p.P, &p.prog);
+      if (rc_) return rc_;
+    }
+  }
+  if (!p.prog) return fail(MPX_ENOPROGRAM, "program_key is NULL");
   if (p.prog->n_phases != p.P) return fail(MPX_EINVAL, "program/phase count mismatch");
-  p.origin = std::string("aot:") + p.prog->key;
+  p.origin += p.prog->key;
+  const bool rt_prog = p.origin[0] == 'n';
 
   // ---- sizes and offsets
   const int nx = p.nx, nu = p.nu, na = p.na, N = p.N, K = p.K, nv = nx + nu + na;
@@ -645,7 +842,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   {
     const char* force = getenv("MPX_KERNEL");
     const bool want_v2 = !(force && strcmp(force, "v1") == 0);
-    const bool want_v3 = force && strcmp(force, "v3") == 0;  // row-block teams: kept for comparison, slower than v2
+    const bool want_v3 = force && strcmp(force, "v3") == 0 && !rt_prog;  // row-block teams: kept for comparison, slower than v2
     auto lw_of = [](int dg) { int lw = 2; while (lw < dg + 1) lw <<= 1; return lw; };
     int stage_cap = 0;  // widest single row-block image over degrees / phases
     for (int dg : p.degs) {

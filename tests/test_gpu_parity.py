@@ -177,3 +177,36 @@ def test_headline_counts(libmpx):
     g = np.empty(tr.n_g)
     assert_close(tr.jac_g_values(z, p, g_out=g), J.data, "headline jac values")
     assert_close(g, ora.g(z, p), "headline g")
+
+
+def test_unregistered_problem_compiles_at_run_time(libmpx):
+    """A problem that is not in problems.REGISTRY: its functors are compiled through NVRTC from the same kernel
+    header, and the result has the same parity with the oracle."""
+    from mpopt_b200 import OCP, ca
+    from mpopt_b200.nlp import Transcription
+    from oracle.nlp import OracleNLP
+
+    ocp = OCP(n_states=3, n_controls=2, n_params=1)
+    ocp.dynamics[0] = lambda x, u, t, a: [x[1] * ca.cos(x[2]) + a[0], u[0] * x[0] - ca.exp(-t) * x[1], u[1] / (2.0 + x[0] ** 2)]
+    ocp.path_constraints[0] = lambda x, u, t, a: [x[0] * x[0] + u[1] - 4.0]
+    ocp.running_costs[0] = lambda x, u, t, a: u[0] * u[0] + ca.sqrt(1.0 + u[1] * u[1]) + a[0] * x[2]
+    ocp.terminal_constraints[0] = lambda xf, tf, x0, t0, a: [xf[0] - 1.0, xf[1] * a[0]]
+    ocp.terminal_costs[0] = lambda xf, tf, x0, t0, a: tf + xf[2] ** 2
+    ocp.lbu[0], ocp.ubu[0] = [-1.0, -2.0], [1.0, 2.0]
+    ocp.a0[0] = [0.5]
+    ocp.validate()
+    K, po = 6, [4, 7, 3, 7, 4, 5]
+    tr = Transcription(ocp, K, po, "LGR", drop_exact_zeros=False)
+    assert tr.program_origin.startswith("nvrtc:")
+    ora = OracleNLP(ocp, K, po, "LGR", drop_exact_zeros=False)
+    z, p = random_point(ora, dirichlet=True)
+    J = ora.jac_g(z, p)
+    rp, ci = tr.structure()
+    assert np.array_equal(rp, J.indptr) and np.array_equal(ci, J.indices)
+    g = np.empty(tr.n_g)
+    assert_close(tr.jac_g_values(z, p, g_out=g), J.data, "jac_g values (nvrtc)")
+    assert_close(g, ora.g(z, p), "g (nvrtc)")
+    assert_close(tr.f(z, p), ora.f(z, p), "f (nvrtc)")
+    assert_close(tr.grad_f(z, p), ora.grad_f(z, p), "grad_f (nvrtc)")
+    tr2 = Transcription(ocp, 3, 5, "CGL")  # second plan of the same program: served from the in-process cache
+    assert tr2.program_origin == tr.program_origin.split(";")[0] + ";" + tr2.program_origin.split(";")[1]
