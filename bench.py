@@ -227,6 +227,19 @@ def run_cuda(args):
         step(i)
     barrier()
 
+    gathered_ok = None
+    if world > 1:  # the gathered buffers must equal a plain single-GPU evaluation, bit for bit (same kernels)
+        full = Transcription(ocp, K, WORKLOAD["poly_orders"], WORKLOAD["scheme"], device=local)
+        g_ref = torch.empty(n_g, dtype=torch.float64, device=dev)
+        v_ref = torch.empty(nnz, dtype=torch.float64, device=dev)
+        step(0)
+        full.g_jac_dev(z_d[0].data_ptr(), p_d.data_ptr(), g_ref.data_ptr(), v_ref.data_ptr(), sp)
+        torch.cuda.synchronize()
+        ok = torch.tensor([int(torch.equal(g_ref, g_d[0]) and torch.equal(v_ref, v_d[0]))], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        gathered_ok = bool(ok.item())
+        del full, g_ref, v_ref
+
     # ---- timed region A (primary): K back-to-back steps over rotating buffer sets, one event pair
     l0 = tr.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -254,7 +267,7 @@ def run_cuda(args):
         b.record(stream)
     torch.cuda.synchronize()
     kern_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    shard_bytes = B if world == 1 else 8 * (n_z + n_p + sum(c for _, c in tr.shard_runs(0)) + sum(c for _, c in tr.shard_runs(1)))
+    shard_bytes = B if world == 1 else int(8 * (n_z + n_p + sum(int(c) for _, c in tr.shard_runs(0)) + sum(int(c) for _, c in tr.shard_runs(1))))
 
     # ---- end-to-end: host buffers through the C ABI (pinned), H2D of z/p and D2H of g/values inside the timing
     e2e = None
@@ -310,6 +323,11 @@ def run_cuda(args):
                      "bytes_per_launch": shard_bytes},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
+    if world > 1:
+        line["gather"] = {"mode": gather.mode, "equals_single_gpu": gathered_ok,
+                          "shard_kernel_us_median": kmed * 1e3,
+                          "note": "value includes the NCCL all-gather of g / Jacobian values to every rank; the shard "
+                                  "kernel alone is shard_kernel_us_median"}
     if cb is not None:
         line["cpu_baseline"] = cb
     print(json.dumps(line))
