@@ -24,7 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
 
-def aot_source(key: str, program) -> str:
+def aot_source(key: str, program, degrees=()) -> str:
     P = program.n_phases
     lines = [
         f"// AOT instantiation of the collocation kernels for program {key} (generated; see mpopt_b200/build.py)",
@@ -34,7 +34,7 @@ def aot_source(key: str, program) -> str:
         "namespace {",
     ]
     for k in range(P):
-        lines.append(f"const MpxAotPhase<MpxPh_{key}_{k}> k_{k};")
+        lines.append(f"const MpxAotPhase<MpxPh_{key}_{k}" + "".join(f", {int(d)}" for d in degrees) + f"> k_{k};")
     lines.append("const MpxPhaseKernels* const phases[] = {" + ", ".join(f"&k_{k}" for k in range(P)) + "};")
     lines.append(f'MpxProgramEntry entry = {{"{key}", {P}, phases, nullptr}};')
     lines.append("struct Reg { Reg() { mpx_register_program(&entry); } } reg;")
@@ -43,21 +43,22 @@ def aot_source(key: str, program) -> str:
 
 
 def generate(verbose=False):
-    from .problems import REGISTRY
+    from .problems import AOT_DEGREES, REGISTRY
     from .program import Program
 
     os.makedirs(GEN, exist_ok=True)
-    wanted = {}
+    wanted, degs = {}, {}
     for name, make in REGISTRY.items():
         prog = Program(make())
         wanted.setdefault(prog.key(), (name, prog))
+        degs[prog.key()] = sorted(set(degs.get(prog.key(), ())) | set(AOT_DEGREES.get(name, ())))
     for fn in os.listdir(GEN):
         if fn.startswith("mpx_aot_") and fn[8:-3] not in wanted:
             os.remove(os.path.join(GEN, fn))
     paths = []
     for key, (name, prog) in wanted.items():
         path = os.path.join(GEN, f"mpx_aot_{key}.cu")
-        src = f"// problem: {name}\n" + aot_source(key, prog)
+        src = f"// problem: {name}\n" + aot_source(key, prog, degs[key])
         if not os.path.exists(path) or open(path).read() != src:
             with open(path, "w") as f:
                 f.write(src)

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <array>
 #include <memory>
 #include <string>
 #include <vector>
@@ -191,9 +192,11 @@ struct mpx_plan {
       d_grad, d_partial, d_f, d_gather, d_evcols, d_unit_k, d_unit_n;
   // v2 (persistent-warp) launch geometry; v2_warps == 0 -> v1 kernel (one CTA per segment)
   int v2_warps = 0, v2_grid = 0, v2_units = 0, v2_stage_cap = 0, v2_smem_jac = 0, v2_smem_g = 0;
-  // v3 (row-block warps): per-phase grid, shared scratch per warp
-  int v3 = 0, num_sms = 0;
-  std::vector<int> v3_grid, v3_threads, v3_smem, v3_smem_g, v3_stage;
+  // v4 (row-block warps, persistent images): per-phase grid, images per warp, shared memory
+  int v4 = 0, num_sms = 0;
+  std::vector<int> v4_grid, v4_threads, v4_smem, v4_smem_g, v4_stage, v4_nbuf;
+  int v4_deg = 0;                  // uniform degree handed to gjac4 (0: generic instance)
+  const void* v4_spec = nullptr;   // RtSpec*: run-time compiled degree-specialised kernels
   std::vector<double> h_p_cache;
   bool p_valid = false;
   const MpxProgramEntry* prog = nullptr;
@@ -354,8 +357,8 @@ RtApi& rt_api() {
 
 // launches through the driver API; same interface as the AOT phases
 struct MpxRtPhase final : MpxPhaseKernels {
-  CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_fgrad[2] = {nullptr, nullptr},
-               f_final[2] = {nullptr, nullptr};
+  CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_gjac4[2] = {nullptr, nullptr},
+               f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr};
   static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
     RtApi& R = rt_api();
     if (smem > 48 * 1024 && R.FuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, 227 * 1024) != 0)
@@ -370,9 +373,10 @@ struct MpxRtPhase final : MpxPhaseKernels {
   cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) const override {
     return go(f_gjac2[jac], a, grid, threads, smem, st);
   }
-  cudaError_t gjac3(const MpxPhaseArgs&, bool, int, int, size_t, cudaStream_t) const override {
-    return cudaErrorNotSupported;
+  cudaError_t gjac4(const MpxPhaseArgs& a, bool jac, int, int grid, int threads, size_t smem, cudaStream_t st) const override {
+    return go(f_gjac4[jac], a, grid, threads, smem, st);  // generic instance; degree-specialised ones: RtSpec
   }
+  bool has_gjac4_degree(int) const override { return false; }
   cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const override {
     return go(f_fgrad[grad], a, grid, MPX_THREADS, smem, st);
   }
@@ -415,9 +419,10 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   if (R.CreateProgram(&prog, src.c_str(), "mpx_rt.cu", 0, nullptr, nullptr) != 0) return fail(MPX_ECUDA, "nvrtcCreateProgram failed");
   std::vector<std::string> names;
   for (int ph = 0; ph < n_phases; ++ph)
-    for (const char* k : {"mpx_gjac_kernel", "mpx_gjac2_kernel", "mpx_fgrad_kernel", "mpx_fgrad_final"})
+    for (const char* k : {"mpx_gjac_kernel", "mpx_gjac2_kernel", "mpx_gjac4_kernel", "mpx_fgrad_kernel", "mpx_fgrad_final"})
       for (const char* b : {"false", "true"})
-        names.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ", " + b + ">");
+        names.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ", " + b +
+                        (strcmp(k, "mpx_gjac4_kernel") == 0 ? ", 0>" : ">"));
   for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   const nvrtcResult_t rc = R.CompileProgram(prog, 3, opts);
@@ -444,8 +449,8 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   size_t idx = 0;
   for (int ph = 0; ph < n_phases; ++ph) {
     std::unique_ptr<MpxRtPhase> P(new MpxRtPhase());
-    CUfunction_t* slots[4] = {P->f_gjac, P->f_gjac2, P->f_fgrad, P->f_final};
-    for (int k = 0; k < 4; ++k)
+    CUfunction_t* slots[5] = {P->f_gjac, P->f_gjac2, P->f_gjac4, P->f_fgrad, P->f_final};
+    for (int k = 0; k < 5; ++k)
       for (int b = 0; b < 2; ++b, ++idx) {
         const char* lowered = nullptr;
         if (R.GetLoweredName(prog, names[idx].c_str(), &lowered) != 0 || !lowered ||
@@ -461,6 +466,82 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   rp->entry = MpxProgramEntry{rp->key.c_str(), n_phases, rp->ptrs.data(), nullptr};
   *out = &rp->entry;
   g_rt_programs.push_back(std::move(rp));
+  return MPX_OK;
+}
+
+// ---- degree-specialised g+jac kernels (mpx_gjac4_kernel<PH, JAC, DEG>) compiled on demand for (program, degree)
+struct RtSpec {
+  std::string key;  // "<program key>:d<deg>"
+  std::vector<std::array<CUfunction_t, 2>> f;  // per phase: [jac]
+};
+std::vector<std::unique_ptr<RtSpec>> g_rt_specs;
+
+const RtSpec* find_rt_spec(const std::string& key) {
+  for (auto& sp : g_rt_specs)
+    if (sp->key == key) return sp.get();
+  return nullptr;
+}
+
+int read_kernel_header(std::string& hdr) {
+  const std::string hdr_path = lib_dir() + "/csrc/mpx_kernels.cuh";
+  FILE* fh = fopen(hdr_path.c_str(), "rb");
+  if (!fh) return fail(MPX_ENOPROGRAM, "cannot read " + hdr_path + " for run-time compilation");
+  char buf[65536];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, fh)) > 0) hdr.append(buf, n);
+  fclose(fh);
+  return MPX_OK;
+}
+
+int compile_spec(const char* key, const char* source, int n_phases, int deg, const RtSpec** out) {
+  RtApi& R = rt_api();
+  if (!R.ok) return fail(MPX_ENOPROGRAM, "NVRTC is unavailable: " + R.err);
+  std::string hdr;
+  int rc0 = read_kernel_header(hdr);
+  if (rc0) return rc0;
+  std::string src = hdr + "\n#define MPX_PHASE_NAME(k) MpxPhRt_##k\n" + source + "\n";
+  nvrtcProgram_t prog = nullptr;
+  if (R.CreateProgram(&prog, src.c_str(), "mpx_rt_spec.cu", 0, nullptr, nullptr) != 0) return fail(MPX_ECUDA, "nvrtcCreateProgram failed");
+  std::vector<std::string> names;
+  for (int ph = 0; ph < n_phases; ++ph)
+    for (const char* b : {"false", "true"})
+      names.push_back("mpx_gjac4_kernel<MpxPhRt_" + std::to_string(ph) + ", " + b + ", " + std::to_string(deg) + ">");
+  for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
+  if (R.CompileProgram(prog, 3, opts) != 0) {
+    size_t ls = 0;
+    R.GetProgramLogSize(prog, &ls);
+    std::string log(ls, '\0');
+    if (ls) R.GetProgramLog(prog, &log[0]);
+    R.DestroyProgram(&prog);
+    return fail(MPX_ECUDA, "NVRTC compilation of the degree-specialised kernel failed:\n" + log.substr(0, 4000));
+  }
+  size_t cs = 0;
+  R.GetCUBINSize(prog, &cs);
+  std::vector<char> cubin(cs);
+  R.GetCUBIN(prog, cubin.data());
+  cudaFree(0);
+  CUmodule_t mod = nullptr;
+  if (R.ModuleLoadData(&mod, cubin.data()) != 0) {
+    R.DestroyProgram(&prog);
+    return fail(MPX_ECUDA, "cuModuleLoadData failed for the degree-specialised kernel");
+  }
+  std::unique_ptr<RtSpec> sp(new RtSpec());
+  sp->key = std::string(key) + ":d" + std::to_string(deg);
+  sp->f.resize(n_phases);
+  size_t idx = 0;
+  for (int ph = 0; ph < n_phases; ++ph)
+    for (int b = 0; b < 2; ++b, ++idx) {
+      const char* lowered = nullptr;
+      if (R.GetLoweredName(prog, names[idx].c_str(), &lowered) != 0 || !lowered ||
+          R.ModuleGetFunction(&sp->f[ph][b], mod, lowered) != 0) {
+        R.DestroyProgram(&prog);
+        return fail(MPX_ECUDA, "kernel " + names[idx] + " not found in the run-time compiled module");
+      }
+    }
+  R.DestroyProgram(&prog);
+  *out = sp.get();
+  g_rt_specs.push_back(std::move(sp));
   return MPX_OK;
 }
 
@@ -842,7 +923,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   {
     const char* force = getenv("MPX_KERNEL");
     const bool want_v2 = !(force && strcmp(force, "v1") == 0);
-    const bool want_v3 = force && strcmp(force, "v3") == 0 && !rt_prog;  // row-block teams: kept for comparison, slower than v2
+    const bool want_v4 = force && strcmp(force, "v4") == 0;  // row-block teams: opt-in until it beats v2 on the headline
     auto lw_of = [](int dg) { int lw = 2; while (lw < dg + 1) lw <<= 1; return lw; };
     int stage_cap = 0;  // widest single row-block image over degrees / phases
     for (int dg : p.degs) {
@@ -880,11 +961,11 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
       CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
       p.num_sms = nsm;
       struct { int multiProcessorCount; } prop{nsm};
-      // v3: CTA = T teams of RT = nx + nc warps; per warp 32 doubles of node values + the image of its row block
-      p.v3_threads.assign(p.P, 0), p.v3_grid.assign(p.P, 0), p.v3_smem.assign(p.P, 0), p.v3_smem_g.assign(p.P, 0);
-      p.v3_stage.assign(p.P, 0);
-      bool ok3 = want_v3;
-      for (int ph = 0; ph < p.P && ok3; ++ph) {
+      // v4: CTA = T teams of RT = nx + nc warps; per warp 32 doubles of node values + nbuf images of its row block
+      p.v4_threads.assign(p.P, 0), p.v4_grid.assign(p.P, 0), p.v4_smem.assign(p.P, 0), p.v4_smem_g.assign(p.P, 0);
+      p.v4_stage.assign(p.P, 0), p.v4_nbuf.assign(p.P, 1);
+      bool ok4 = want_v4;
+      for (int ph = 0; ph < p.P && ok4; ++ph) {
         const int RT = nx + p.ph[ph].nc;
         int img = 0;  // widest row-block image over degrees
         for (int dg : p.degs) {
@@ -893,19 +974,54 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
           for (int c = 0; c < p.ph[ph].nc; ++c) img = std::max(img, rows_cap * p.ph[ph].c_len[c]);
         }
         img = MpxTab::pad2(img);
-        if (RT < 1 || RT > MPX3_MAX_THREADS / 32) { ok3 = false; break; }
-        const int T = std::max(1, std::min(8 / RT, (int)((uk.size() + p.num_sms - 1) / p.num_sms)));
+        const int max_warps = MPX4_MAX_THREADS / 32;
+        if (RT < 1 || RT > max_warps) { ok4 = false; break; }
+        const long fixed = (long)(p.tab_doubles + 2) * 8, lim = 227L * 1024;
+        auto smem_of = [&](int warps, int nbuf) {  // per warp: two ring slots of node values + nbuf images
+          return fixed + (long)warps * (2L * (nx + nu) * 32 + (long)nbuf * (img + 2)) * 8;
+        };
+        const int units_per_sm = (int)((uk.size() + p.num_sms - 1) / p.num_sms);
+        int T = std::max(1, std::min(max_warps / RT, units_per_sm));
+        if (const char* tenv = getenv("MPX_V4_TEAMS")) T = std::max(1, std::min(max_warps / RT, atoi(tenv)));
+        while (T > 1 && smem_of(RT * T, 1) > lim) --T;
+        if (smem_of(RT * T, 1) > lim) { ok4 = false; break; }
+        int nbuf = smem_of(RT * T, 2) <= lim ? 2 : 1;
+        // two images per warp beat more teams when both do not fit: drop teams while that keeps >= 8 warps
+        if (nbuf == 1 && !getenv("MPX_V4_TEAMS")) {
+          int T2 = T;
+          while (T2 > 1 && smem_of(RT * T2, 2) > lim) --T2;
+          if (smem_of(RT * T2, 2) <= lim && RT * T2 >= 8) T = T2, nbuf = 2;
+        }
+        if (const char* benv = getenv("MPX_V4_NBUF")) {
+          const int want = atoi(benv) >= 2 ? 2 : 1;
+          if (smem_of(RT * T, want) <= lim) nbuf = want;
+        }
         const int warps = RT * T;
-        const long smem = (long)(p.tab_doubles + 2 + (long)warps * (32 + img)) * 8;
-        if (smem > 227L * 1024) { ok3 = false; break; }
-        // resident CTAs per SM: shared memory, and ~20 warps (96 registers per thread)
-        const int per_sm = (int)std::max<long>(1, std::min<long>(std::min<long>(227L * 1024 / (smem + 1024), std::max(1, 20 / warps)), 8));
-        p.v3_threads[ph] = warps * 32, p.v3_stage[ph] = img;
-        p.v3_smem[ph] = (int)smem;
-        p.v3_smem_g[ph] = (int)((p.tab_doubles + 2 + (long)warps * 32) * 8);
-        p.v3_grid[ph] = (int)std::max<long>(1, std::min<long>((long)per_sm * p.num_sms, ((long)uk.size() + T - 1) / T));
+        p.v4_threads[ph] = warps * 32, p.v4_stage[ph] = img, p.v4_nbuf[ph] = nbuf;
+        p.v4_smem[ph] = (int)smem_of(warps, nbuf);
+        p.v4_smem_g[ph] = (int)smem_of(warps, 0);
+        p.v4_grid[ph] = (int)std::max<long>(1, std::min<long>(p.num_sms, ((long)uk.size() + T - 1) / T));
       }
-      p.v3 = ok3 ? 1 : 0;
+      p.v4 = ok4 ? 1 : 0;
+      // degree-specialised instance: compiled in (AOT list of the problem), or through NVRTC for large plans
+      if (ok4 && p.uniform) {
+        const int dg = p.po[0];
+        bool aot = true;
+        for (int ph = 0; ph < p.P; ++ph) aot = aot && p.prog->phases[ph]->has_gjac4_degree(dg);
+        const char* jit = getenv("MPX_JIT");
+        const bool want_jit = jit ? atoi(jit) != 0 : (long)(p.seg_end - p.seg_begin) * dg >= 16384;
+        if (aot && !(jit && atoi(jit) < 0)) {
+          p.v4_deg = dg;
+        } else if (want_jit && d->program_source && d->program_key) {
+          const std::string skey = std::string(d->program_key) + ":d" + std::to_string(dg);
+          const RtSpec* sp = find_rt_spec(skey);
+          if (!sp) {
+            int rc_ = compile_spec(d->program_key, d->program_source, p.P, dg, &sp);
+            if (rc_) return rc_;
+          }
+          p.v4_spec = sp;
+        }
+      }
       p.v2_units = (int)uk.size();
       p.v2_warps = std::max(1, std::min(warps, (p.v2_units + prop.multiProcessorCount - 1) / prop.multiProcessorCount));
       p.v2_grid = std::min(prop.multiProcessorCount, (p.v2_units + p.v2_warps - 1) / p.v2_warps);
@@ -919,7 +1035,9 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
 
   if (p.v2_warps == 0 && p.smem_too_big)
     return fail(MPX_ELIMIT, "segment too large for the shared-memory staged kernels (degree x states)");
-  p.origin += p.v3 ? ";gjac=v3" : (p.v2_warps > 0 ? ";gjac=v2" : ";gjac=v1");
+  p.origin += p.v4 ? ";gjac=v4" : (p.v2_warps > 0 ? ";gjac=v2" : ";gjac=v1");
+  if (p.v4 && p.v4_deg) p.origin += "/d" + std::to_string(p.v4_deg);
+  if (p.v4 && p.v4_spec) p.origin += "/jit-d" + std::to_string(p.po[0]);
 
   // ---- kernel arguments per phase (pointers filled per call)
   p.args.resize(p.P);
@@ -1079,9 +1197,13 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     MpxPhaseArgs& a = p.args[ph];
     a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
     a.g = d_g, a.vals = target;
-    if (p.v3) {
-      a.stage_cap = p.v3_stage[ph];
-      CUDA_TRY(p.prog->phases[ph]->gjac3(a, jac, p.v3_grid[ph], p.v3_threads[ph], jac ? p.v3_smem[ph] : p.v3_smem_g[ph], st));
+    if (p.v4) {
+      a.stage_cap = p.v4_stage[ph], a.v4_nbuf = p.v4_nbuf[ph];
+      const size_t sm4 = jac ? p.v4_smem[ph] : p.v4_smem_g[ph];
+      if (p.v4_spec)
+        CUDA_TRY(MpxRtPhase::go(static_cast<const RtSpec*>(p.v4_spec)->f[ph][jac], a, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
+      else
+        CUDA_TRY(p.prog->phases[ph]->gjac4(a, jac, p.v4_deg, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
     } else if (p.v2_warps > 0)
       CUDA_TRY(p.prog->phases[ph]->gjac2(a, jac, p.v2_grid, p.v2_warps * 32, jac ? p.v2_smem_jac : p.v2_smem_g, st));
     else

@@ -15,8 +15,10 @@ struct MpxPhaseKernels {
   virtual cudaError_t gjac(const MpxPhaseArgs& a, bool jac, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem,
                             cudaStream_t st) const = 0;
-  virtual cudaError_t gjac3(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem,
+  // deg > 0: use the instance specialised for that uniform degree if there is one (see has_gjac4_degree)
+  virtual cudaError_t gjac4(const MpxPhaseArgs& a, bool jac, int deg, int grid, int threads, size_t smem,
                             cudaStream_t st) const = 0;
+  virtual bool has_gjac4_degree(int deg) const = 0;
   virtual cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const = 0;
 };
@@ -32,7 +34,7 @@ extern "C" void mpx_register_program(MpxProgramEntry* e);
 const MpxProgramEntry* mpx_find_program(const char* key);
 
 // AOT implementation: direct <<<>>> launches of the template instantiations
-template <class PH>
+template <class PH, int... DEGS>
 struct MpxAotPhase final : MpxPhaseKernels {
   template <class K>
   static cudaError_t allow_smem(K kern, size_t smem, bool& done) {
@@ -68,19 +70,33 @@ struct MpxAotPhase final : MpxPhaseKernels {
     }
     return cudaGetLastError();
   }
-  cudaError_t gjac3(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem,
-                    cudaStream_t st) const override {
+  template <int DEG>
+  static cudaError_t launch4(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) {
     static bool d0 = false, d1 = false;
     cudaError_t e;
     if (jac) {
-      if ((e = allow_smem(mpx_gjac3_kernel<PH, true>, smem, d1)) != cudaSuccess) return e;
-      mpx_gjac3_kernel<PH, true><<<grid, threads, smem, st>>>(a);
+      if ((e = allow_smem(mpx_gjac4_kernel<PH, true, DEG>, smem, d1)) != cudaSuccess) return e;
+      mpx_gjac4_kernel<PH, true, DEG><<<grid, threads, smem, st>>>(a);
     } else {
-      if ((e = allow_smem(mpx_gjac3_kernel<PH, false>, smem, d0)) != cudaSuccess) return e;
-      mpx_gjac3_kernel<PH, false><<<grid, threads, smem, st>>>(a);
+      if ((e = allow_smem(mpx_gjac4_kernel<PH, false, DEG>, smem, d0)) != cudaSuccess) return e;
+      mpx_gjac4_kernel<PH, false, DEG><<<grid, threads, smem, st>>>(a);
     }
     return cudaGetLastError();
   }
+  template <int D0, int... REST>
+  static cudaError_t pick4(int deg, const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) {
+    if constexpr (sizeof...(REST) == 0) {
+      return launch4<D0>(a, jac, grid, threads, smem, st);  // the list ends with 0 = generic
+    } else {
+      if (deg == D0) return launch4<D0>(a, jac, grid, threads, smem, st);
+      return pick4<REST...>(deg, a, jac, grid, threads, smem, st);
+    }
+  }
+  cudaError_t gjac4(const MpxPhaseArgs& a, bool jac, int deg, int grid, int threads, size_t smem,
+                    cudaStream_t st) const override {
+    return pick4<DEGS..., 0>(deg, a, jac, grid, threads, smem, st);
+  }
+  bool has_gjac4_degree(int deg) const override { return deg > 0 && (... || (deg == DEGS)); }
   cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const override {
     static bool d0 = false, d1 = false;
     cudaError_t e;

@@ -175,6 +175,16 @@ __global__ void __launch_bounds__(MPX_TAB_THREADS) mpx_tables_kernel(int scheme,
     C[e] = v;
     rec[MpxTab::off_Ct(n1) + j * d + m] = v;
   }
+  // replicated constant blocks (one bulk store per work unit of the warp kernels): smax copies of Cmid and of D[1:, :]
+  const int smax = MpxTab::smax(n1);
+  if (smax > 1) {
+    __syncthreads();  // D and C of this record are complete (same CTA wrote them)
+    for (int e = threadIdx.x; e < smax * d * n1; e += blockDim.x) {
+      const int w = e % (d * n1);
+      rec[MpxTab::off_Cr(n1) + e] = C[w];
+      rec[MpxTab::off_Dr(n1) + e] = D[n1 + w];
+    }
+  }
 }
 
 // basis (order 0) or its derivatives (order 1|2) at arbitrary points: out[n_taus][n1]

@@ -205,3 +205,12 @@ REGISTRY = {
     "synthetic_6_3": synthetic_6_3,
     "kitchen_sink": kitchen_sink,
 }
+
+#: uniform polynomial degrees for which build() also compiles the degree-specialised g + jac_g kernel
+#: (mpx_gjac4_kernel<PH, JAC, DEG>) of a registered problem; any other uniform degree is specialised at plan
+#: creation through NVRTC when the plan is large, and runs the generic instance otherwise
+AOT_DEGREES = {
+    "synthetic_6_3": (15, 20),   # BASELINE.json headline (p=15) and the sharded configuration (p=20)
+    "moon_lander": (15,),        # BASELINE.json configs[1]
+    "two_phase_schwartz": (10,), # stand-in for BASELINE.json configs[4]
+}
