@@ -189,7 +189,7 @@ def run_cuda(args):
     p_d = torch.from_numpy(p_h).to(dev)
     g_d = [torch.empty(n_g, dtype=torch.float64, device=dev) for _ in range(R)]
     v_d = [torch.empty(nnz, dtype=torch.float64, device=dev) for _ in range(R)]
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
+    flush = torch.zeros(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
     stream = torch.cuda.Stream()  # a real (non-NULL) stream: events and kernels share it (NULL = plan's own stream)
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
@@ -254,11 +254,14 @@ def run_cuda(args):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
 
-    # ---- timed region B (kernel alone, L2 flushed before every launch): roofline numerator
+    # ---- timed region B (one launch at a time, L2 evicted before each): context for the roofline.  The eviction is a
+    #      READ of 256 MB (clean lines): filling L2 with dirty lines instead would charge their write-back to the kernel.
     kern_ms = []
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    nb = min(args.steps, 50)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nb)]
+    sink = torch.empty(1, dtype=torch.float64, device=dev)
     for i, (a, b) in enumerate(ev):
-        flush.fill_(float(i))
+        torch.sum(flush, dim=0, keepdim=True, out=sink)
         a.record(stream)
         tr.g_jac_dev(z_d[i % R].data_ptr(), p_d.data_ptr(), g_d[i % R].data_ptr(), v_d[i % R].data_ptr(), sp)
         b.record(stream)
@@ -297,7 +300,10 @@ def run_cuda(args):
     else:
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     kmed = float(np.median(kern_ms))
-    achieved = shard_bytes / (kmed * 1e-3) / 1e9
+    # roofline: algorithmic bytes of one launch / average launch duration over timed region A (CUDA events on the launch
+    # stream around K back-to-back launches whose outputs rotate over 4 sets = 437 MB > L2, so every launch streams to HBM)
+    launch_ms = ms_step if world == 1 else kmed
+    achieved = shard_bytes / (launch_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -310,14 +316,16 @@ def run_cuda(args):
         "config": {"workload": "synthetic 6-state/3-control quadratic-dynamics OCP (SURVEY 8d), n_segments=4096, "
                                "poly_orders=15, LGR: one fused g + jac_g evaluation per step",
                    "n_z": n_z, "n_g": n_g, "nnz_jac": nnz, "algorithmic_bytes": B,
-                   "l2": f"value: {R} rotating z/g/values sets ({R * B / 1e6:.0f} MB > 126 MB L2), launches back to back; "
-                         "roofline: L2 flushed (256 MB fill) before every timed launch",
+                   "l2": f"{R} rotating z/g/values sets ({R * B / 1e6:.0f} MB > 126 MB L2), launches back to back",
                    "parallelism": "1 GPU" if world == 1 else f"segments sharded over {world} GPUs + NCCL all-gather of g/values",
                    "program": tr.program_origin},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "kernel": "mpx_gjac_kernel<synthetic_6_3, JAC>",
-                     "kernel_us_median": kmed * 1e3, "kernel_us_min": float(kern_ms.min()) * 1e3,
-                     "bytes_per_launch": shard_bytes},
+                     "traffic": traffic, "peak_source": peak_src, "kernel": "mpx_gjac2_kernel<synthetic_6_3, JAC, 15>",
+                     "launch_us_avg": launch_ms * 1e3, "bytes_per_launch": shard_bytes,
+                     "isolated_launch_us_median": kmed * 1e3, "isolated_launch_us_min": float(kern_ms.min()) * 1e3,
+                     "how": "achieved = algorithmic bytes / average launch duration over the timed region (back-to-back "
+                            "launches, rotating output sets > L2); isolated_* = single launches after a 256 MB read that "
+                            "evicts L2 (includes launch latency and a cold start)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
     if world > 1:

@@ -191,12 +191,12 @@ struct mpx_plan {
   DevBuf d_tabs, d_seg_tab, d_seg_start, d_seg_dpre, d_seg_ipre, d_seg_spre, d_z, d_p, d_sig0, d_g, d_vals, d_full,
       d_grad, d_partial, d_f, d_gather, d_evcols, d_unit_k, d_unit_n;
   // v2 (persistent-warp) launch geometry; v2_warps == 0 -> v1 kernel (one CTA per segment)
-  int v2_warps = 0, v2_grid = 0, v2_units = 0, v2_stage_cap = 0, v2_smem_jac = 0, v2_smem_g = 0;
+  int v2_warps = 0, v2_grid = 0, v2_units = 0, v2_stage_cap = 0, v2_smem_jac = 0, v2_smem_g = 0, v2_nbuf = 1;
   // v4 (row-block warps, persistent images): per-phase grid, images per warp, shared memory
   int v4 = 0, num_sms = 0;
   std::vector<int> v4_grid, v4_threads, v4_smem, v4_smem_g, v4_stage, v4_nbuf;
-  int v4_deg = 0;                  // uniform degree handed to gjac4 (0: generic instance)
-  const void* v4_spec = nullptr;   // RtSpec*: run-time compiled degree-specialised kernels
+  int spec_deg = 0;                // uniform degree handed to gjac2 / gjac4 (0: generic instance)
+  const void* rt_spec = nullptr;   // RtSpec*: run-time compiled degree-specialised kernels
   std::vector<double> h_p_cache;
   bool p_valid = false;
   const MpxProgramEntry* prog = nullptr;
@@ -370,13 +370,13 @@ struct MpxRtPhase final : MpxPhaseKernels {
   cudaError_t gjac(const MpxPhaseArgs& a, bool jac, int grid, size_t smem, cudaStream_t st) const override {
     return go(f_gjac[jac], a, grid, MPX_THREADS, smem, st);
   }
-  cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) const override {
-    return go(f_gjac2[jac], a, grid, threads, smem, st);
+  cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int, int grid, int threads, size_t smem, cudaStream_t st) const override {
+    return go(f_gjac2[jac], a, grid, threads, smem, st);  // generic instance; degree-specialised ones: RtSpec
   }
   cudaError_t gjac4(const MpxPhaseArgs& a, bool jac, int, int grid, int threads, size_t smem, cudaStream_t st) const override {
     return go(f_gjac4[jac], a, grid, threads, smem, st);  // generic instance; degree-specialised ones: RtSpec
   }
-  bool has_gjac4_degree(int) const override { return false; }
+  bool has_degree(int) const override { return false; }
   cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const override {
     return go(f_fgrad[grad], a, grid, MPX_THREADS, smem, st);
   }
@@ -422,7 +422,7 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
     for (const char* k : {"mpx_gjac_kernel", "mpx_gjac2_kernel", "mpx_gjac4_kernel", "mpx_fgrad_kernel", "mpx_fgrad_final"})
       for (const char* b : {"false", "true"})
         names.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ", " + b +
-                        (strcmp(k, "mpx_gjac4_kernel") == 0 ? ", 0>" : ">"));
+                        (strcmp(k, "mpx_gjac4_kernel") == 0 || strcmp(k, "mpx_gjac2_kernel") == 0 ? ", 0>" : ">"));
   for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   const nvrtcResult_t rc = R.CompileProgram(prog, 3, opts);
@@ -469,9 +469,9 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   return MPX_OK;
 }
 
-// ---- degree-specialised g+jac kernels (mpx_gjac4_kernel<PH, JAC, DEG>) compiled on demand for (program, degree)
+// ---- degree-specialised g+jac kernels (mpx_gjac2_kernel / mpx_gjac4_kernel<PH, JAC, DEG>) compiled on demand
 struct RtSpec {
-  std::string key;  // "<program key>:d<deg>"
+  std::string key;  // "<program key>:<kernel>:d<deg>"
   std::vector<std::array<CUfunction_t, 2>> f;  // per phase: [jac]
 };
 std::vector<std::unique_ptr<RtSpec>> g_rt_specs;
@@ -493,7 +493,7 @@ int read_kernel_header(std::string& hdr) {
   return MPX_OK;
 }
 
-int compile_spec(const char* key, const char* source, int n_phases, int deg, const RtSpec** out) {
+int compile_spec(const char* key, const char* source, int n_phases, int deg, const char* kernel, const RtSpec** out) {
   RtApi& R = rt_api();
   if (!R.ok) return fail(MPX_ENOPROGRAM, "NVRTC is unavailable: " + R.err);
   std::string hdr;
@@ -505,7 +505,7 @@ int compile_spec(const char* key, const char* source, int n_phases, int deg, con
   std::vector<std::string> names;
   for (int ph = 0; ph < n_phases; ++ph)
     for (const char* b : {"false", "true"})
-      names.push_back("mpx_gjac4_kernel<MpxPhRt_" + std::to_string(ph) + ", " + b + ", " + std::to_string(deg) + ">");
+      names.push_back(std::string(kernel) + "<MpxPhRt_" + std::to_string(ph) + ", " + b + ", " + std::to_string(deg) + ">");
   for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   if (R.CompileProgram(prog, 3, opts) != 0) {
@@ -527,7 +527,7 @@ int compile_spec(const char* key, const char* source, int n_phases, int deg, con
     return fail(MPX_ECUDA, "cuModuleLoadData failed for the degree-specialised kernel");
   }
   std::unique_ptr<RtSpec> sp(new RtSpec());
-  sp->key = std::string(key) + ":d" + std::to_string(deg);
+  sp->key = std::string(key) + ":" + kernel + ":d" + std::to_string(deg);
   sp->f.resize(n_phases);
   size_t idx = 0;
   for (int ph = 0; ph < n_phases; ++ph)
@@ -935,7 +935,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     }
     stage_cap = MpxTab::pad2(stage_cap);
     const long avail = 227L * 1024 - (long)(p.tab_doubles + 2) * 8;
-    const long per_warp = (long)(32 * (nx + nu) + stage_cap) * 8;
+    long per_warp = (long)(32 * (nx + nu) + stage_cap + 2) * 8;  // node values + one row-block image
     int warps = (int)std::min<long>(MPX2_MAX_THREADS / 32, avail > 0 ? avail / per_warp : 0);
     if (const char* wenv = getenv("MPX_V2_WARPS")) warps = std::max(1, std::min(warps, atoi(wenv)));
     if (want_v2 && dmax <= 31 && warps >= 1 && p.tab_doubles * 8L <= 96L * 1024) {
@@ -1004,28 +1004,33 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
       }
       p.v4 = ok4 ? 1 : 0;
       // degree-specialised instance: compiled in (AOT list of the problem), or through NVRTC for large plans
-      if (ok4 && p.uniform) {
+      if (p.uniform && !getenv("MPX_NOSPEC")) {
         const int dg = p.po[0];
         bool aot = true;
-        for (int ph = 0; ph < p.P; ++ph) aot = aot && p.prog->phases[ph]->has_gjac4_degree(dg);
+        for (int ph = 0; ph < p.P; ++ph) aot = aot && p.prog->phases[ph]->has_degree(dg);
         const char* jit = getenv("MPX_JIT");
         const bool want_jit = jit ? atoi(jit) != 0 : (long)(p.seg_end - p.seg_begin) * dg >= 16384;
+        const char* kname = ok4 ? "mpx_gjac4_kernel" : "mpx_gjac2_kernel";
         if (aot && !(jit && atoi(jit) < 0)) {
-          p.v4_deg = dg;
+          p.spec_deg = dg;
         } else if (want_jit && d->program_source && d->program_key) {
-          const std::string skey = std::string(d->program_key) + ":d" + std::to_string(dg);
+          const std::string skey = std::string(d->program_key) + ":" + kname + ":d" + std::to_string(dg);
           const RtSpec* sp = find_rt_spec(skey);
           if (!sp) {
-            int rc_ = compile_spec(d->program_key, d->program_source, p.P, dg, &sp);
+            int rc_ = compile_spec(d->program_key, d->program_source, p.P, dg, kname, &sp);
             if (rc_) return rc_;
           }
-          p.v4_spec = sp;
+          p.rt_spec = sp;
         }
       }
       p.v2_units = (int)uk.size();
       p.v2_warps = std::max(1, std::min(warps, (p.v2_units + prop.multiProcessorCount - 1) / prop.multiProcessorCount));
       p.v2_grid = std::min(prop.multiProcessorCount, (p.v2_units + p.v2_warps - 1) / p.v2_warps);
       p.v2_stage_cap = stage_cap;
+      // a second image per warp (the engine drains one while the next is assembled) when it fits
+      p.v2_nbuf = (long)p.v2_warps * (per_warp + (long)(stage_cap + 2) * 8) <= avail ? 2 : 1;
+      if (const char* benv = getenv("MPX_V2_NBUF")) p.v2_nbuf = (atoi(benv) >= 2 && p.v2_nbuf == 2) ? 2 : 1;
+      if (p.v2_nbuf == 2) per_warp += (long)(stage_cap + 2) * 8;
       p.v2_smem_jac = (int)((p.tab_doubles + 2) * 8 + p.v2_warps * per_warp);
       p.v2_smem_g = (int)((p.tab_doubles + 2) * 8 + p.v2_warps * (long)(32 * (nx + nu)) * 8);
       CUDA_TRY(up(p.d_unit_k, uk.data(), uk.size() * sizeof(int32_t)));
@@ -1036,8 +1041,8 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   if (p.v2_warps == 0 && p.smem_too_big)
     return fail(MPX_ELIMIT, "segment too large for the shared-memory staged kernels (degree x states)");
   p.origin += p.v4 ? ";gjac=v4" : (p.v2_warps > 0 ? ";gjac=v2" : ";gjac=v1");
-  if (p.v4 && p.v4_deg) p.origin += "/d" + std::to_string(p.v4_deg);
-  if (p.v4 && p.v4_spec) p.origin += "/jit-d" + std::to_string(p.po[0]);
+  if ((p.v4 || p.v2_warps > 0) && p.spec_deg) p.origin += "/d" + std::to_string(p.spec_deg);
+  if ((p.v4 || p.v2_warps > 0) && p.rt_spec) p.origin += "/jit-d" + std::to_string(p.po[0]);
 
   // ---- kernel arguments per phase (pointers filled per call)
   p.args.resize(p.P);
@@ -1055,7 +1060,6 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     a.unit_k = p.d_unit_k.as<int32_t>(), a.unit_n = p.d_unit_n.as<int32_t>();
     a.n_units = p.v2_units, a.tab_doubles = p.tab_doubles, a.stage_cap = p.v2_stage_cap;
     a.flags = (L.has_DU ? MPX_F_DU : 0) | (L.has_mU ? MPX_F_MU : 0) | (p.seg_end == K ? MPX_F_TAIL : 0);
-    if (const char* dbg = getenv("MPX_DEBUG_FLAGS")) a.flags |= atoi(dbg) & (MPX_F_DBG_NOSTORE | MPX_F_DBG_STOREONLY);
     a.accumulate_f = ph > 0;
     a.zoff = L.zoff;
     a.gF = L.gF, a.gC = L.gC, a.gDU = L.gDU, a.gmU = L.gmU, a.gTC = L.gTC;
@@ -1200,12 +1204,18 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     if (p.v4) {
       a.stage_cap = p.v4_stage[ph], a.v4_nbuf = p.v4_nbuf[ph];
       const size_t sm4 = jac ? p.v4_smem[ph] : p.v4_smem_g[ph];
-      if (p.v4_spec)
-        CUDA_TRY(MpxRtPhase::go(static_cast<const RtSpec*>(p.v4_spec)->f[ph][jac], a, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
+      if (p.rt_spec)
+        CUDA_TRY(MpxRtPhase::go(static_cast<const RtSpec*>(p.rt_spec)->f[ph][jac], a, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
       else
-        CUDA_TRY(p.prog->phases[ph]->gjac4(a, jac, p.v4_deg, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
-    } else if (p.v2_warps > 0)
-      CUDA_TRY(p.prog->phases[ph]->gjac2(a, jac, p.v2_grid, p.v2_warps * 32, jac ? p.v2_smem_jac : p.v2_smem_g, st));
+        CUDA_TRY(p.prog->phases[ph]->gjac4(a, jac, p.spec_deg, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
+    } else if (p.v2_warps > 0) {
+      a.v4_nbuf = p.v2_nbuf;
+      const size_t sm2 = jac ? p.v2_smem_jac : p.v2_smem_g;
+      if (p.rt_spec)
+        CUDA_TRY(MpxRtPhase::go(static_cast<const RtSpec*>(p.rt_spec)->f[ph][jac], a, p.v2_grid, p.v2_warps * 32, sm2, st));
+      else
+        CUDA_TRY(p.prog->phases[ph]->gjac2(a, jac, p.spec_deg, p.v2_grid, p.v2_warps * 32, sm2, st));
+    }
     else
       CUDA_TRY(p.prog->phases[ph]->gjac(a, jac, grid, jac ? p.smem_gjac : p.smem_g, st));
     ++p.launches;

@@ -13,12 +13,12 @@
 struct MpxPhaseKernels {
   virtual ~MpxPhaseKernels() {}
   virtual cudaError_t gjac(const MpxPhaseArgs& a, bool jac, int grid, size_t smem, cudaStream_t st) const = 0;
-  virtual cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem,
+  // deg > 0: use the instance specialised for that uniform degree if there is one (see has_degree)
+  virtual cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int deg, int grid, int threads, size_t smem,
                             cudaStream_t st) const = 0;
-  // deg > 0: use the instance specialised for that uniform degree if there is one (see has_gjac4_degree)
   virtual cudaError_t gjac4(const MpxPhaseArgs& a, bool jac, int deg, int grid, int threads, size_t smem,
                             cudaStream_t st) const = 0;
-  virtual bool has_gjac4_degree(int deg) const = 0;
+  virtual bool has_degree(int deg) const = 0;
   virtual cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const = 0;
 };
@@ -57,18 +57,31 @@ struct MpxAotPhase final : MpxPhaseKernels {
     }
     return cudaGetLastError();
   }
-  cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem,
-                    cudaStream_t st) const override {
+  template <int DEG>
+  static cudaError_t launch2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) {
     static bool d0 = false, d1 = false;
     cudaError_t e;
     if (jac) {
-      if ((e = allow_smem(mpx_gjac2_kernel<PH, true>, smem, d1)) != cudaSuccess) return e;
-      mpx_gjac2_kernel<PH, true><<<grid, threads, smem, st>>>(a);
+      if ((e = allow_smem(mpx_gjac2_kernel<PH, true, DEG>, smem, d1)) != cudaSuccess) return e;
+      mpx_gjac2_kernel<PH, true, DEG><<<grid, threads, smem, st>>>(a);
     } else {
-      if ((e = allow_smem(mpx_gjac2_kernel<PH, false>, smem, d0)) != cudaSuccess) return e;
-      mpx_gjac2_kernel<PH, false><<<grid, threads, smem, st>>>(a);
+      if ((e = allow_smem(mpx_gjac2_kernel<PH, false, DEG>, smem, d0)) != cudaSuccess) return e;
+      mpx_gjac2_kernel<PH, false, DEG><<<grid, threads, smem, st>>>(a);
     }
     return cudaGetLastError();
+  }
+  template <int D0, int... REST>
+  static cudaError_t pick2(int deg, const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) {
+    if constexpr (sizeof...(REST) == 0) {
+      return launch2<D0>(a, jac, grid, threads, smem, st);  // the list ends with 0 = generic
+    } else {
+      if (deg == D0) return launch2<D0>(a, jac, grid, threads, smem, st);
+      return pick2<REST...>(deg, a, jac, grid, threads, smem, st);
+    }
+  }
+  cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int deg, int grid, int threads, size_t smem,
+                    cudaStream_t st) const override {
+    return pick2<DEGS..., 0>(deg, a, jac, grid, threads, smem, st);
   }
   template <int DEG>
   static cudaError_t launch4(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) {
@@ -96,7 +109,7 @@ struct MpxAotPhase final : MpxPhaseKernels {
                     cudaStream_t st) const override {
     return pick4<DEGS..., 0>(deg, a, jac, grid, threads, smem, st);
   }
-  bool has_gjac4_degree(int deg) const override { return deg > 0 && (... || (deg == DEGS)); }
+  bool has_degree(int deg) const override { return deg > 0 && (... || (deg == DEGS)); }
   cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const override {
     static bool d0 = false, d1 = false;
     cudaError_t e;
