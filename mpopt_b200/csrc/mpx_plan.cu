@@ -227,6 +227,15 @@ static int compute_tables(int scheme, const std::vector<int>& degs, const std::v
   return MPX_OK;
 }
 
+extern "C" int mpx_pdl_enabled(void) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MPX_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v;
+}
+
 static int check_degree(int scheme, int deg) {
   if (scheme < MPX_LGR || scheme > MPX_CGL) return fail(MPX_EINVAL, "unknown collocation scheme");
   if (deg < 1 || deg > MPX_MAX_DEG) return fail(MPX_ELIMIT, "polynomial degree must be in [1, 200]");
@@ -317,6 +326,23 @@ struct RtApi {
   CUresult_t (*FuncSetAttribute)(CUfunction_t, int, int);
   CUresult_t (*LaunchKernel)(CUfunction_t, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*,
                              void**, void**);
+  CUresult_t (*LaunchKernelEx)(const void* /*CUlaunchConfig*/, CUfunction_t, void**, void**);  // may be null
+};
+
+// mirrors of CUlaunchConfig / CUlaunchAttribute (cuda.h, CUDA 12): only the fields used here
+struct RtLaunchAttr {
+  int id;              // CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION = 6
+  char pad[8 - sizeof(int)];
+  union {
+    char raw[64];
+    int programmaticStreamSerializationAllowed;
+  } value;
+};
+struct RtLaunchConfig {
+  unsigned gridDimX, gridDimY, gridDimZ, blockDimX, blockDimY, blockDimZ, sharedMemBytes;
+  void* hStream;
+  RtLaunchAttr* attrs;
+  unsigned numAttrs;
 };
 
 template <class F>
@@ -352,6 +378,7 @@ RtApi& rt_api() {
            load_sym(hc, "cuModuleGetFunction", api.ModuleGetFunction, api.err) &&
            load_sym(hc, "cuFuncSetAttribute", api.FuncSetAttribute, api.err) &&
            load_sym(hc, "cuLaunchKernel", api.LaunchKernel, api.err);
+  api.LaunchKernelEx = reinterpret_cast<decltype(api.LaunchKernelEx)>(dlsym(hc, "cuLaunchKernelEx"));
   return api;
 }
 
@@ -359,11 +386,20 @@ RtApi& rt_api() {
 struct MpxRtPhase final : MpxPhaseKernels {
   CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_gjac4[2] = {nullptr, nullptr},
                f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr};
-  static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+  static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st,
+                        bool pdl = false) {
     RtApi& R = rt_api();
     if (smem > 48 * 1024 && R.FuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, 227 * 1024) != 0)
       return cudaErrorInvalidValue;
     void* params[] = {const_cast<MpxPhaseArgs*>(&a)};
+    if (pdl && R.LaunchKernelEx && mpx_pdl_enabled()) {
+      RtLaunchAttr at;
+      memset(&at, 0, sizeof at);
+      at.id = 6;  // CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION
+      at.value.programmaticStreamSerializationAllowed = 1;
+      RtLaunchConfig cfg = {(unsigned)grid, 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, st, &at, 1};
+      return R.LaunchKernelEx(&cfg, f, params, nullptr) == 0 ? cudaSuccess : cudaErrorLaunchFailure;
+    }
     return R.LaunchKernel(f, grid, 1, 1, threads, 1, 1, (unsigned)smem, st, params, nullptr) == 0 ? cudaSuccess
                                                                                                 : cudaErrorLaunchFailure;
   }
@@ -371,7 +407,7 @@ struct MpxRtPhase final : MpxPhaseKernels {
     return go(f_gjac[jac], a, grid, MPX_THREADS, smem, st);
   }
   cudaError_t gjac2(const MpxPhaseArgs& a, bool jac, int, int grid, int threads, size_t smem, cudaStream_t st) const override {
-    return go(f_gjac2[jac], a, grid, threads, smem, st);  // generic instance; degree-specialised ones: RtSpec
+    return go(f_gjac2[jac], a, grid, threads, smem, st, true);  // generic instance; degree-specialised ones: RtSpec
   }
   cudaError_t gjac4(const MpxPhaseArgs& a, bool jac, int, int grid, int threads, size_t smem, cudaStream_t st) const override {
     return go(f_gjac4[jac], a, grid, threads, smem, st);  // generic instance; degree-specialised ones: RtSpec
@@ -1060,6 +1096,10 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     a.unit_k = p.d_unit_k.as<int32_t>(), a.unit_n = p.d_unit_n.as<int32_t>();
     a.n_units = p.v2_units, a.tab_doubles = p.tab_doubles, a.stage_cap = p.v2_stage_cap;
     a.flags = (L.has_DU ? MPX_F_DU : 0) | (L.has_mU ? MPX_F_MU : 0) | (p.seg_end == K ? MPX_F_TAIL : 0);
+    // constant blocks before the row blocks: the copy engine has work from the moment the tables land, one memory
+    // round trip before the first image is ready (MPX_CONST_FIRST=0 restores the old order, for measurements)
+    const char* cf = getenv("MPX_CONST_FIRST");
+    if (!cf || atoi(cf)) a.flags |= MPX_F_CONST_FIRST;
     a.accumulate_f = ph > 0;
     a.zoff = L.zoff;
     a.gF = L.gF, a.gC = L.gC, a.gDU = L.gDU, a.gmU = L.gmU, a.gTC = L.gTC;
@@ -1212,7 +1252,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
       a.v4_nbuf = p.v2_nbuf;
       const size_t sm2 = jac ? p.v2_smem_jac : p.v2_smem_g;
       if (p.rt_spec)
-        CUDA_TRY(MpxRtPhase::go(static_cast<const RtSpec*>(p.rt_spec)->f[ph][jac], a, p.v2_grid, p.v2_warps * 32, sm2, st));
+        CUDA_TRY(MpxRtPhase::go(static_cast<const RtSpec*>(p.rt_spec)->f[ph][jac], a, p.v2_grid, p.v2_warps * 32, sm2, st, true));
       else
         CUDA_TRY(p.prog->phases[ph]->gjac2(a, jac, p.spec_deg, p.v2_grid, p.v2_warps * 32, sm2, st));
     }

@@ -31,6 +31,7 @@ struct MpxProgramEntry {
 };
 
 extern "C" void mpx_register_program(MpxProgramEntry* e);
+extern "C" int mpx_pdl_enabled(void);  // MPX_PDL=0 turns programmatic dependent launch off
 const MpxProgramEntry* mpx_find_program(const char* key);
 
 // AOT implementation: direct <<<>>> launches of the template instantiations
@@ -57,18 +58,27 @@ struct MpxAotPhase final : MpxPhaseKernels {
     }
     return cudaGetLastError();
   }
+  // launch with the programmatic-stream-serialization attribute (see mpx_pdl_wait in mpx_kernels.cuh)
+  template <class K>
+  static cudaError_t launch_pdl(K kern, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = mpx_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a);
+  }
   template <int DEG>
   static cudaError_t launch2(const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) {
     static bool d0 = false, d1 = false;
     cudaError_t e;
     if (jac) {
       if ((e = allow_smem(mpx_gjac2_kernel<PH, true, DEG>, smem, d1)) != cudaSuccess) return e;
-      mpx_gjac2_kernel<PH, true, DEG><<<grid, threads, smem, st>>>(a);
-    } else {
-      if ((e = allow_smem(mpx_gjac2_kernel<PH, false, DEG>, smem, d0)) != cudaSuccess) return e;
-      mpx_gjac2_kernel<PH, false, DEG><<<grid, threads, smem, st>>>(a);
+      return launch_pdl(mpx_gjac2_kernel<PH, true, DEG>, a, grid, threads, smem, st);
     }
-    return cudaGetLastError();
+    if ((e = allow_smem(mpx_gjac2_kernel<PH, false, DEG>, smem, d0)) != cudaSuccess) return e;
+    return launch_pdl(mpx_gjac2_kernel<PH, false, DEG>, a, grid, threads, smem, st);
   }
   template <int D0, int... REST>
   static cudaError_t pick2(int deg, const MpxPhaseArgs& a, bool jac, int grid, int threads, size_t smem, cudaStream_t st) {

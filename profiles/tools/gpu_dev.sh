@@ -5,7 +5,7 @@ OUT=gpurun_out/$TAG
 mkdir -p $OUT
 ( timeout 900 python -m pytest tests -x -q -m gpu ) > $OUT/pytest_gpu.log 2>&1
 tail -15 $OUT/pytest_gpu.log
-for cfg in "v2" "v2 MPX_V2_NBUF=1" "v2 MPX_NOSPEC=1" "v2 MPX_NOSPEC=1 MPX_V2_NBUF=1"; do
+for cfg in "v2" "v2 MPX_JIT=-1" "v2 MPX_NOSPEC=1"; do
   set -- $cfg
   echo "== $cfg"
   env MPX_KERNEL=$1 $2 $3 timeout 300 python bench.py --no-cpu --steps 200 2>&1 | python -c "
