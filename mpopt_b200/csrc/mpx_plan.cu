@@ -389,8 +389,14 @@ struct MpxRtPhase final : MpxPhaseKernels {
   static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st,
                         bool pdl = false) {
     RtApi& R = rt_api();
-    if (smem > 48 * 1024 && R.FuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, 227 * 1024) != 0)
-      return cudaErrorInvalidValue;
+    if (smem > 48 * 1024) {  // opt in to large dynamic shared memory once per function, not once per launch
+      static std::vector<CUfunction_t> configured;
+      if (std::find(configured.begin(), configured.end(), f) == configured.end()) {
+        if (R.FuncSetAttribute(f, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, 227 * 1024) != 0)
+          return cudaErrorInvalidValue;
+        configured.push_back(f);
+      }
+    }
     void* params[] = {const_cast<MpxPhaseArgs*>(&a)};
     if (pdl && R.LaunchKernelEx && mpx_pdl_enabled()) {
       RtLaunchAttr at;
