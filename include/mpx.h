@@ -140,6 +140,62 @@ int mpx_eval_g_jac_dev(mpx_plan* plan, const double* d_z, const double* d_p, dou
                        void* stream);
 int mpx_sync(mpx_plan* plan);
 
+/* -- staged evaluation: ONE upload and ONE fused evaluation per distinct x, results kept in the plan's device
+ *    buffers; the pieces are copied out when asked for. This is how the solver-facing shims below honour IPOPT's
+ *    new_x flag (eval_g and eval_jac_g of the same x share one kernel launch) and how CasADi's nlp_jac_g gets its
+ *    values in column-compressed order (device gather through the static permutation of mpx_jac_structure_ccs). */
+#define MPX_STAGE_F 1
+#define MPX_STAGE_GRAD 2
+#define MPX_STAGE_G 4
+#define MPX_STAGE_JAC 8
+#define MPX_FETCH_JAC_CCS 16 /* mpx_fetch only: Jacobian values in CCS order */
+int mpx_stage(mpx_plan* plan, const double* z, const double* p, int32_t what /* MPX_STAGE_* bits */);
+int mpx_staged(const mpx_plan* plan);                       /* bits valid for the x of the last mpx_stage */
+int mpx_fetch(mpx_plan* plan, int32_t what, double* out);   /* F: 1, GRAD: n_z, G: n_g, JAC / JAC_CCS: nnz doubles */
+
+/* -- IPOPT C interface (IpStdCInterface.h: Eval_F_CB, Eval_Grad_F_CB, Eval_G_CB, Eval_Jac_G_CB): pass these four
+ *    functions to CreateIpoptProblem and a filled mpx_ipopt_data as user_data. Index = int, Number = double,
+ *    Bool = int (only the low byte of new_x is read, so a C99 bool works too); index_style 0 (C). eval_jac_g with
+ *    values == NULL writes the CSR pattern as triplets. No Eval_H_CB: use hessian_approximation limited-memory. */
+typedef struct mpx_ipopt_data {
+  mpx_plan* plan;
+  const double* p;  /* segment-width fractions (the NLP parameter vector, mpopt.py:631) */
+} mpx_ipopt_data;
+int mpx_ipopt_eval_f(int n, const double* x, int new_x, double* obj_value, void* user_data);
+int mpx_ipopt_eval_grad_f(int n, const double* x, int new_x, double* grad_f, void* user_data);
+int mpx_ipopt_eval_g(int n, const double* x, int new_x, int m, double* g, void* user_data);
+int mpx_ipopt_eval_jac_g(int n, const double* x, int new_x, int m, int nele_jac, int* iRow, int* jCol, double* values,
+                         void* user_data);
+
+/* -- CasADi external functions (the ABI of CasADi's generated C code, as loaded by ca.external(name, lib) and by
+ *    ca.nlpsol(name, plugin, lib)): nlp_f (x,p)->(f), nlp_g (x,p)->(g), nlp_grad_f (x,p)->(f, grad_f_x),
+ *    nlp_jac_g (x,p)->(g, jac_g_x in CCS) -- the functions ca.nlpsol derives at mpopt.py:757. The symbols are fixed
+ *    by that ABI, so they evaluate the plan bound with mpx_casadi_bind (one plan at a time per process). Each
+ *    NAME comes with NAME_n_in/_n_out/_name_in/_name_out/_sparsity_in/_sparsity_out/_work/_incref/_decref/
+ *    _alloc_mem/_init_mem/_free_mem/_checkout/_release/_default_in (declared in mpx_casadi.h style below). */
+int mpx_casadi_bind(mpx_plan* plan);
+#define MPX_CASADI_DECLARE(NAME)                                                                      \
+  int NAME(const double** arg, double** res, long long* iw, double* w, int mem);                      \
+  long long NAME##_n_in(void);                                                                        \
+  long long NAME##_n_out(void);                                                                       \
+  double NAME##_default_in(long long i);                                                              \
+  const char* NAME##_name_in(long long i);                                                            \
+  const char* NAME##_name_out(long long i);                                                           \
+  const long long* NAME##_sparsity_in(long long i);                                                   \
+  const long long* NAME##_sparsity_out(long long i);                                                  \
+  int NAME##_work(long long* sz_arg, long long* sz_res, long long* sz_iw, long long* sz_w);           \
+  int NAME##_alloc_mem(void);                                                                         \
+  int NAME##_init_mem(int mem);                                                                       \
+  void NAME##_free_mem(int mem);                                                                      \
+  int NAME##_checkout(void);                                                                          \
+  void NAME##_release(int mem);                                                                       \
+  void NAME##_incref(void);                                                                           \
+  void NAME##_decref(void);
+MPX_CASADI_DECLARE(nlp_f)
+MPX_CASADI_DECLARE(nlp_g)
+MPX_CASADI_DECLARE(nlp_grad_f)
+MPX_CASADI_DECLARE(nlp_jac_g)
+
 /* number of kernel launches issued by this plan so far (bench.py's gpu_launches) */
 int64_t mpx_launch_count(const mpx_plan* plan);
 /* human-readable description of how the node functors were obtained ("aot:<key>" / "nvrtc:<key>") */

@@ -36,6 +36,19 @@ class ProblemDesc(C.Structure):
                 ("seg_end", C.c_int32)]
 
 
+class IpoptData(C.Structure):
+    """mpx_ipopt_data: user_data of the IPOPT C-interface callbacks."""
+    _fields_ = [("plan", C.c_void_p), ("p", c_f64p)]
+
+
+MPX_STAGE_F, MPX_STAGE_GRAD, MPX_STAGE_G, MPX_STAGE_JAC, MPX_FETCH_JAC_CCS = 1, 2, 4, 8, 16
+
+#: CasADi external-function symbols exported for each of these names (include/mpx.h, MPX_CASADI_DECLARE)
+CASADI_FUNCTIONS = ("nlp_f", "nlp_g", "nlp_grad_f", "nlp_jac_g")
+CASADI_SUFFIXES = ("", "_n_in", "_n_out", "_default_in", "_name_in", "_name_out", "_sparsity_in", "_sparsity_out",
+                   "_work", "_alloc_mem", "_init_mem", "_free_mem", "_checkout", "_release", "_incref", "_decref")
+
+
 class MpxError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libmpx error {code}: {msg}")
@@ -65,6 +78,15 @@ PROTOTYPES = {
     "mpx_eval_jac_g": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p]),
     "mpx_eval_f_grad_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpx_eval_g_jac_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpx_stage": (C.c_int, [C.c_void_p, c_f64p, c_f64p, C.c_int32]),
+    "mpx_staged": (C.c_int, [C.c_void_p]),
+    "mpx_fetch": (C.c_int, [C.c_void_p, C.c_int32, c_f64p]),
+    "mpx_ipopt_eval_f": (C.c_int, [C.c_int, c_f64p, C.c_int, c_f64p, C.c_void_p]),
+    "mpx_ipopt_eval_grad_f": (C.c_int, [C.c_int, c_f64p, C.c_int, c_f64p, C.c_void_p]),
+    "mpx_ipopt_eval_g": (C.c_int, [C.c_int, c_f64p, C.c_int, C.c_int, c_f64p, C.c_void_p]),
+    "mpx_ipopt_eval_jac_g": (C.c_int, [C.c_int, c_f64p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_int), c_f64p, C.c_void_p]),
+    "mpx_casadi_bind": (C.c_int, [C.c_void_p]),
     "mpx_sync": (C.c_int, [C.c_void_p]),
     "mpx_launch_count": (C.c_int64, [C.c_void_p]),
     "mpx_program_origin": (C.c_char_p, [C.c_void_p]),

@@ -106,7 +106,7 @@ def _compile(src, force):
 def build(force=False, verbose=False):
     """Generate + compile + link.  Returns the path of libmpx.so."""
     os.makedirs(OBJ, exist_ok=True)
-    srcs = [os.path.join(CSRC, "mpx_plan.cu")] + generate(verbose)
+    srcs = [os.path.join(CSRC, "mpx_plan.cu"), os.path.join(CSRC, "mpx_shims.cu")] + generate(verbose)
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         results = list(ex.map(lambda s: _compile(s, force), srcs))
     objs = [o for o, _ in results]

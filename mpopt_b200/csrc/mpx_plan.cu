@@ -199,6 +199,9 @@ struct mpx_plan {
   const void* rt_spec = nullptr;   // RtSpec*: run-time compiled degree-specialised kernels
   std::vector<double> h_p_cache;
   bool p_valid = false;
+  std::vector<int64_t> h_runs[3];  // shard plans: (offset, count) runs of g / values / grad_f written by this shard
+  int staged = 0;                  // MPX_STAGE_* results currently valid in the device buffers (mpx_stage / mpx_fetch)
+  DevBuf d_ccs_perm, d_ccs_vals;   // CCS order of the Jacobian values, built on first use
   const MpxProgramEntry* prog = nullptr;
   std::string origin;
   std::vector<MpxPhaseArgs> args;
@@ -1315,10 +1318,50 @@ static int launch_f_grad(mpx_plan& p, const double* d_z, const double* d_p, doub
   return MPX_OK;
 }
 
+// device -> host copy of a result vector: whole for a full plan, only the runs this shard writes for a shard plan
+// (the caller's array is full-size; other shards fill the rest -- each GPU moves its part over its own PCIe link)
+static int download(mpx_plan& p, int kind, double* dst, const double* src, size_t n_full) {
+  const bool shard = p.seg_begin != 0 || p.seg_end != p.K;
+  if (!shard || (kind == 1 && !p.gather.empty())) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n_full * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+    return MPX_OK;
+  }
+  std::vector<int64_t>& runs = p.h_runs[kind];
+  if (runs.empty()) {
+    int64_t n = 0;
+    int rc = mpx_shard_runs(&p, kind, nullptr, &n);
+    if (rc) return rc;
+    runs.resize((size_t)2 * n);
+    rc = mpx_shard_runs(&p, kind, runs.data(), &n);
+    if (rc) return rc;
+  }
+  for (size_t i = 0; i + 1 < runs.size(); i += 2)
+    CUDA_TRY(cudaMemcpyAsync(dst + runs[i], src + runs[i], (size_t)runs[i + 1] * sizeof(double), cudaMemcpyDeviceToHost,
+                             p.stream));
+  return MPX_OK;
+}
+
 static int upload_inputs(mpx_plan& p, const double* z, const double* pw) {
   if (!z || !pw) return fail(MPX_EINVAL, "z and p must not be NULL");
   CUDA_TRY(cudaSetDevice(p.device));
-  CUDA_TRY(cudaMemcpyAsync(p.d_z.p, z, (size_t)p.n_z * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+  if (p.seg_begin == 0 && p.seg_end == p.K) {
+    CUDA_TRY(cudaMemcpyAsync(p.d_z.p, z, (size_t)p.n_z * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+  } else {  // a shard reads only its own nodes (plus the node it shares with the previous segment) and t0 / tf / a
+    // (one segment more at the end: the slope-continuity row of the last boundary reads the next segment's nodes)
+    const int64_t nb = p.seg_start[p.seg_begin], cnt = p.seg_start[std::min(p.seg_end + 1, p.K)] - nb + 1, nv = p.nx + p.nu;
+    double* dz = p.d_z.as<double>();
+    for (int ph = 0; ph < p.P; ++ph) {
+      const int64_t off = p.ph[ph].zoff;
+      for (int64_t v = 0; v < nv; ++v)
+        CUDA_TRY(cudaMemcpyAsync(dz + off + v * p.N + nb, z + off + v * p.N + nb, (size_t)cnt * sizeof(double),
+                                 cudaMemcpyHostToDevice, p.stream));
+      CUDA_TRY(cudaMemcpyAsync(dz + off + nv * p.N, z + off + nv * p.N, (size_t)(2 + p.na) * sizeof(double),
+                               cudaMemcpyHostToDevice, p.stream));
+      if (p.seg_begin > 0)  // terminal rows (last shard) and the slope-continuity rows also read the first node
+        for (int64_t v = 0; v < nv; ++v)
+          CUDA_TRY(cudaMemcpyAsync(dz + off + v * p.N, z + off + v * p.N, sizeof(double), cudaMemcpyHostToDevice, p.stream));
+    }
+  }
   if (!p.p_valid || memcmp(p.h_p_cache.data(), pw, (size_t)p.n_p * sizeof(double)) != 0) {
     p.h_p_cache.assign(pw, pw + p.n_p);
     CUDA_TRY(cudaMemcpyAsync(p.d_p.p, p.h_p_cache.data(), (size_t)p.n_p * sizeof(double), cudaMemcpyHostToDevice, p.stream));
@@ -1333,7 +1376,8 @@ extern "C" int mpx_eval_g(mpx_plan* p, const double* z, const double* pw, double
   if (rc) return rc;
   rc = launch_g_jac(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_g.as<double>(), nullptr, p->stream);
   if (rc) return rc;
-  CUDA_TRY(cudaMemcpyAsync(g, p->d_g.p, (size_t)p->n_g * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  rc = download(*p, 0, g, p->d_g.as<double>(), (size_t)p->n_g);
+  if (rc) return rc;
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;
 }
@@ -1344,8 +1388,8 @@ extern "C" int mpx_eval_jac_g(mpx_plan* p, const double* z, const double* pw, do
   if (rc) return rc;
   rc = launch_g_jac(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_g.as<double>(), p->d_vals.as<double>(), p->stream);
   if (rc) return rc;
-  if (g) CUDA_TRY(cudaMemcpyAsync(g, p->d_g.p, (size_t)p->n_g * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
-  CUDA_TRY(cudaMemcpyAsync(values, p->d_vals.p, (size_t)p->nnz * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (g && (rc = download(*p, 0, g, p->d_g.as<double>(), (size_t)p->n_g))) return rc;
+  if ((rc = download(*p, 1, values, p->d_vals.as<double>(), (size_t)p->nnz))) return rc;
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;
 }
@@ -1369,6 +1413,63 @@ extern "C" int mpx_eval_grad_f(mpx_plan* p, const double* z, const double* pw, d
   if (rc) return rc;
   if (f) CUDA_TRY(cudaMemcpyAsync(f, p->d_f.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaMemcpyAsync(grad, p->d_grad.p, (size_t)p->n_z * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+// ------------------------------------------------------------------ staged evaluation (one upload, one fused
+// evaluation per distinct x; the callers -- IPOPT / CasADi shims -- fetch the pieces they are asked for)
+extern "C" int mpx_stage(mpx_plan* p, const double* z, const double* pw, int32_t what) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  if (what & ~(MPX_STAGE_F | MPX_STAGE_GRAD | MPX_STAGE_G | MPX_STAGE_JAC)) return fail(MPX_EINVAL, "unknown MPX_STAGE_* bit");
+  p->staged = 0;
+  int rc = upload_inputs(*p, z, pw);
+  if (rc) return rc;
+  if (what & (MPX_STAGE_G | MPX_STAGE_JAC)) {
+    rc = launch_g_jac(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_g.as<double>(),
+                      (what & MPX_STAGE_JAC) ? p->d_vals.as<double>() : nullptr, p->stream);
+    if (rc) return rc;
+  }
+  if (what & (MPX_STAGE_F | MPX_STAGE_GRAD)) {
+    rc = launch_f_grad(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_f.as<double>(),
+                       (what & MPX_STAGE_GRAD) ? p->d_grad.as<double>() : nullptr, p->stream);
+    if (rc) return rc;
+  }
+  p->staged = what | ((what & MPX_STAGE_JAC) ? MPX_STAGE_G : 0) | ((what & MPX_STAGE_GRAD) ? MPX_STAGE_F : 0);
+  return MPX_OK;
+}
+
+extern "C" int mpx_staged(const mpx_plan* p) { return p ? p->staged : 0; }
+
+extern "C" int mpx_fetch(mpx_plan* p, int32_t what, double* out) {
+  if (!p || !out) return fail(MPX_EINVAL, "NULL argument");
+  const int base = what == MPX_FETCH_JAC_CCS ? MPX_STAGE_JAC : what;
+  if (base != MPX_STAGE_F && base != MPX_STAGE_GRAD && base != MPX_STAGE_G && base != MPX_STAGE_JAC)
+    return fail(MPX_EINVAL, "mpx_fetch takes exactly one MPX_STAGE_* bit (or MPX_FETCH_JAC_CCS)");
+  if (!(p->staged & base)) return fail(MPX_EINVAL, "mpx_fetch: that result has not been staged for the current x");
+  CUDA_TRY(cudaSetDevice(p->device));
+  const void* src = nullptr;
+  size_t n = 0;
+  if (what == MPX_STAGE_F) src = p->d_f.p, n = 1;
+  else if (what == MPX_STAGE_GRAD) src = p->d_grad.p, n = (size_t)p->n_z;
+  else if (what == MPX_STAGE_G) src = p->d_g.p, n = (size_t)p->n_g;
+  else if (what == MPX_STAGE_JAC) src = p->d_vals.p, n = (size_t)p->nnz;
+  else {  // CasADi's column-compressed order: gather on the device through the static permutation
+    if (!p->d_ccs_perm.p) {
+      std::vector<int64_t> perm((size_t)p->nnz);
+      int rc = mpx_jac_structure_ccs(p, nullptr, nullptr, perm.data());
+      if (rc) return rc;
+      CUDA_TRY(p->d_ccs_perm.ensure(perm.size() * sizeof(int64_t)));
+      CUDA_TRY(p->d_ccs_vals.ensure(perm.size() * sizeof(double)));
+      CUDA_TRY(cudaMemcpy(p->d_ccs_perm.p, perm.data(), perm.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    }
+    mpx_compact_kernel<<<(unsigned)((p->nnz + 255) / 256), 256, 0, p->stream>>>(p->d_vals.as<double>(), p->d_ccs_perm.as<int64_t>(),
+                                                                              p->d_ccs_vals.as<double>(), p->nnz);
+    CUDA_TRY(cudaGetLastError());
+    ++p->launches;
+    src = p->d_ccs_vals.p, n = (size_t)p->nnz;
+  }
+  CUDA_TRY(cudaMemcpyAsync(out, src, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;
 }

@@ -1,0 +1,132 @@
+"""Solver-facing shims of include/mpx.h: IPOPT's C-interface callbacks and CasADi's external-function ABI.
+
+CPU part: every symbol is exported and refuses to compute without a bound plan.  GPU part: the callbacks, driven
+through their C calling conventions exactly as IPOPT / CasADi would, return what the oracle computes (the reference's
+nlp_f / nlp_grad_f / nlp_g / nlp_jac_g, /root/reference/mpopt/mpopt.py:757, :804)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from helpers import assert_close, random_point
+
+
+def test_casadi_symbols_exported(libmpx):
+    from mpopt_b200 import _lib
+
+    for name in _lib.CASADI_FUNCTIONS:
+        for suf in _lib.CASADI_SUFFIXES:
+            assert getattr(libmpx, name + suf) is not None
+    libmpx.nlp_jac_g_n_in.restype = libmpx.nlp_jac_g_n_out.restype = C.c_longlong
+    assert libmpx.nlp_jac_g_n_in() == 2 and libmpx.nlp_jac_g_n_out() == 2
+    libmpx.nlp_grad_f_name_out.restype = C.c_char_p
+    libmpx.nlp_grad_f_name_out.argtypes = [C.c_longlong]
+    assert libmpx.nlp_grad_f_name_out(1) == b"grad_f_x"
+    # nothing bound: no sparsity, evaluation reports failure (non-zero), nothing is computed on the host
+    assert libmpx.mpx_casadi_bind(None) == 0
+    libmpx.nlp_g_sparsity_in.restype = C.c_void_p
+    libmpx.nlp_g_sparsity_in.argtypes = [C.c_longlong]
+    assert libmpx.nlp_g_sparsity_in(0) is None
+    assert libmpx.nlp_g(None, None, None, None, 0) != 0
+
+
+def test_ipopt_callbacks_reject_missing_plan(libmpx):
+    from mpopt_b200 import _lib
+
+    x, out = np.zeros(4), np.zeros(4)
+    assert libmpx.mpx_ipopt_eval_f(4, _lib.ptr(x), 1, _lib.ptr(out), None) == 0
+    d = _lib.IpoptData(None, None)
+    assert libmpx.mpx_ipopt_eval_g(4, _lib.ptr(x), 1, 4, _lib.ptr(out), C.byref(d)) == 0
+    assert libmpx.mpx_stage(None, None, None, 0) == _lib.MPX_EINVAL
+    assert libmpx.mpx_fetch(None, 4, None) == _lib.MPX_EINVAL
+
+
+def _setup(make, K, p, scheme):
+    from mpopt_b200.nlp import Transcription
+    from oracle.nlp import OracleNLP
+
+    ocp = make()
+    tr = Transcription(ocp, K, p, scheme, drop_exact_zeros=False)
+    ora = OracleNLP(ocp, K, p, scheme, drop_exact_zeros=False)
+    z, w = random_point(ora, dirichlet=True)
+    return tr, ora, z, w
+
+
+@pytest.mark.gpu
+def test_ipopt_callbacks_match_oracle(libmpx):
+    from mpopt_b200 import _lib
+    from mpopt_b200.problems import kitchen_sink
+
+    tr, ora, z, w = _setup(kitchen_sink, 4, [3, 5, 4, 3], "LGR")
+    n, m, nnz = tr.n_z, tr.n_g, tr.nnz
+    d = _lib.IpoptData(tr._plan, _lib.ptr(w))
+    ud = C.byref(d)
+    # structure request (values == NULL): triplets in CSR order, C indexing
+    ir, jc = np.zeros(nnz, np.int32), np.zeros(nnz, np.int32)
+    ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int))
+    assert libmpx.mpx_ipopt_eval_jac_g(n, _lib.ptr(z), 1, m, nnz, ip(ir), ip(jc), None, ud) == 1
+    J = ora.jac_g(z, w)
+    assert np.array_equal(jc, J.indices) and np.array_equal(ir, np.repeat(np.arange(m), np.diff(J.indptr)))
+    # IPOPT's call order for one iterate: f (new_x), grad_f, g, jac_g (same x) -> one fused evaluation
+    f, grad, g, vals = np.zeros(1), np.zeros(n), np.zeros(m), np.zeros(nnz)
+    l0 = tr.launches
+    assert libmpx.mpx_ipopt_eval_f(n, _lib.ptr(z), 1, _lib.ptr(f), ud) == 1
+    l1 = tr.launches
+    assert libmpx.mpx_ipopt_eval_grad_f(n, _lib.ptr(z), 0, _lib.ptr(grad), ud) == 1
+    assert libmpx.mpx_ipopt_eval_g(n, _lib.ptr(z), 0, m, _lib.ptr(g), ud) == 1
+    assert libmpx.mpx_ipopt_eval_jac_g(n, _lib.ptr(z), 0, m, nnz, None, None, _lib.ptr(vals), ud) == 1
+    assert l1 > l0 and tr.launches == l1, "new_x = 0 must not launch anything"
+    assert abs(f[0] - ora.f(z, w)) <= 1e-10 * max(1.0, abs(ora.f(z, w)))
+    assert_close(grad, ora.grad_f(z, w), "grad_f")
+    assert_close(g, ora.g(z, w), "g")
+    assert_close(vals, J.data, "jac_g values")
+    # a new point
+    z2 = z + 1e-3
+    assert libmpx.mpx_ipopt_eval_g(n, _lib.ptr(z2), 1, m, _lib.ptr(g), ud) == 1
+    assert_close(g, ora.g(z2, w), "g at the second point")
+    # wrong sizes are refused
+    assert libmpx.mpx_ipopt_eval_g(n + 1, _lib.ptr(z), 1, m, _lib.ptr(g), ud) == 0
+
+
+@pytest.mark.gpu
+def test_casadi_externals_match_oracle(libmpx):
+    from mpopt_b200 import _lib
+    from mpopt_b200.problems import two_phase_schwartz
+
+    tr, ora, z, w = _setup(two_phase_schwartz, 3, 4, "LGL")
+    n, m, nnz = tr.n_z, tr.n_g, tr.nnz
+    assert libmpx.mpx_casadi_bind(tr._plan) == 0
+    try:
+        # sparsity of jac_g_x: compact CCS [nrow, ncol, colind, row] == the oracle's pattern
+        libmpx.nlp_jac_g_sparsity_out.restype = C.POINTER(C.c_longlong)
+        libmpx.nlp_jac_g_sparsity_out.argtypes = [C.c_longlong]
+        sp = libmpx.nlp_jac_g_sparsity_out(1)
+        Jc = ora.jac_g(z, w).tocsc()
+        Jc.sort_indices()
+        assert (sp[0], sp[1]) == (m, n)
+        colind = np.array([sp[2 + i] for i in range(n + 1)])
+        rows = np.array([sp[2 + n + 1 + i] for i in range(nnz)])
+        assert np.array_equal(colind, Jc.indptr) and np.array_equal(rows, Jc.indices)
+        sx = libmpx.nlp_jac_g_sparsity_out(0)
+        assert (sx[0], sx[1], sx[3]) == (m, 1, m)
+        # evaluation through (arg, res, iw, w, mem)
+        arg = (C.POINTER(C.c_double) * 2)(_lib.ptr(z), _lib.ptr(w))
+        g, jv, f, grad = np.zeros(m), np.zeros(nnz), np.zeros(1), np.zeros(n)
+        res = (C.POINTER(C.c_double) * 2)(_lib.ptr(g), _lib.ptr(jv))
+        assert libmpx.nlp_jac_g(arg, res, None, None, 0) == 0
+        assert_close(g, ora.g(z, w), "nlp_jac_g: g")
+        assert_close(jv, Jc.data, "nlp_jac_g: jac_g_x (CCS order)")
+        res = (C.POINTER(C.c_double) * 2)(_lib.ptr(f), _lib.ptr(grad))
+        assert libmpx.nlp_grad_f(arg, res, None, None, 0) == 0
+        assert abs(f[0] - ora.f(z, w)) <= 1e-10 * max(1.0, abs(ora.f(z, w)))
+        assert_close(grad, ora.grad_f(z, w), "nlp_grad_f")
+        g[:] = 0
+        res1 = (C.POINTER(C.c_double) * 1)(_lib.ptr(g))
+        assert libmpx.nlp_g(arg, res1, None, None, 0) == 0
+        assert_close(g, ora.g(z, w), "nlp_g")
+        f[:] = 0
+        res1 = (C.POINTER(C.c_double) * 1)(_lib.ptr(f))
+        assert libmpx.nlp_f(arg, res1, None, None, 0) == 0
+        assert abs(f[0] - ora.f(z, w)) <= 1e-10 * max(1.0, abs(ora.f(z, w)))
+    finally:
+        libmpx.mpx_casadi_bind(None)
