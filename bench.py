@@ -253,9 +253,53 @@ def run_cuda(args):
     torch.cuda.synchronize()
     kern_ms = np.array([a.elapsed_time(b) for a, b in ev])
 
-    # ---- N > 1: the north-star variant -- one NCCL all-gather of the shards' g / CSR value blocks per evaluation
-    allgather = None
+    # ---- N > 1: the north-star variant -- every rank ends up with the whole g / Jacobian.  (a) fused: the kernel's
+    #      stores go to the peers' buffers as well (peer memory over NVLink, no separate collective, one tiny all-reduce
+    #      per evaluation orders the ranks); (b) baseline: the same shards + one NCCL all-gather of g / CSR values.
+    allgather = allgather_nccl = None
     if world > 1 and not args.no_allgather:
+        def verify(g_t, v_t):  # equal to a plain single-GPU evaluation of the whole NLP, bit for bit
+            full = Transcription(ocp, Kt, deg, scheme, device=local)
+            g_ref = torch.empty(n_g, dtype=torch.float64, device=dev)
+            v_ref = torch.empty(nnz, dtype=torch.float64, device=dev)
+            full.g_jac_dev(z_d[0].data_ptr(), p_d.data_ptr(), g_ref.data_ptr(), v_ref.data_ptr(), sp)
+            torch.cuda.synchronize()
+            okt = torch.tensor([int(torch.equal(g_ref, g_t) and torch.equal(v_ref, v_t))], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            return bool(okt.item())
+
+        ng = max(3, min(args.steps, 20))
+        recv = 8 * (world - 1) * own  # bytes every rank receives per evaluation
+        # (a) fused peer stores
+        pb = sh.PeerBuffers(n_g, nnz, dist, rank, local, n_sets=R)
+        flag = torch.zeros(1, device=dev)
+
+        def fstep(i):
+            k = i % R
+            g_t, v_t = pb.local(k)
+            pg, pv = pb.peers(k)
+            tr.g_jac_dev_peers(z_d[k].data_ptr(), p_d.data_ptr(), g_t.data_ptr(), v_t.data_ptr(), pg, pv, sp)
+            dist.all_reduce(flag)  # every rank's kernel (and with it its peer stores) has completed
+
+        for i in range(3):
+            fstep(i)
+        barrier()
+        fstep(0)
+        torch.cuda.synchronize()
+        ok = verify(*pb.local(0)) if world <= 2 else None
+        barrier()
+        e0.record(stream)
+        for i in range(ng):
+            fstep(i)
+        e1.record(stream)
+        barrier()
+        ms_f = max_over_ranks(e0.elapsed_time(e1)) / ng
+        allgather = {"value": world * 1e3 / ms_f, "unit": UNIT, "ms_per_step": ms_f, "steps": ng, "equals_single_gpu": ok,
+                     "bytes_sent_per_rank": int(recv), "nvlink_gbs_per_rank": recv / (ms_f * 1e-3) / 1e9,
+                     "how": "mpx_eval_g_jac_dev_peers: each image is handed to the copy engine once per destination "
+                            "(cp.async.bulk to peer-mapped memory), g by plain peer stores; + one 4-byte all-reduce"}
+        pb.close()
+        # (b) NCCL baseline
         row0 = None
         z_cur = [z_d[0]]
         if rank != 0:  # global node 0's rows are recomputed locally instead of being broadcast (mpopt_b200/shard.py)
@@ -272,19 +316,9 @@ def run_cuda(args):
         for i in range(3):
             gstep(i)
         barrier()
-        ok = None
-        if world <= 2:  # the gathered buffers equal a plain single-GPU evaluation of the whole NLP, bit for bit
-            full = Transcription(ocp, Kt, deg, scheme, device=local)
-            g_ref = torch.empty(n_g, dtype=torch.float64, device=dev)
-            v_ref = torch.empty(nnz, dtype=torch.float64, device=dev)
-            gstep(0)
-            full.g_jac_dev(z_d[0].data_ptr(), p_d.data_ptr(), g_ref.data_ptr(), v_ref.data_ptr(), sp)
-            torch.cuda.synchronize()
-            okt = torch.tensor([int(torch.equal(g_ref, g_d[0]) and torch.equal(v_ref, v_d[0]))], device=dev)
-            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-            ok = bool(okt.item())
-            del full, g_ref, v_ref
-        ng = max(3, min(args.steps, 20))
+        gstep(0)
+        torch.cuda.synchronize()
+        ok = verify(g_d[0], v_d[0]) if world <= 2 else None
         barrier()
         e0.record(stream)
         for i in range(ng):
@@ -292,11 +326,9 @@ def run_cuda(args):
         e1.record(stream)
         barrier()
         ms_g = max_over_ranks(e0.elapsed_time(e1)) / ng
-        recv = 8 * (world - 1) * (K * deg * ((tr.nx + tr.nu)) + (nnz // world))  # ~ bytes every rank receives
-        allgather = {"value": world * 1e3 / ms_g, "unit": UNIT, "ms_per_step": ms_g, "steps": ng, "mode": gather.mode,
-                     "equals_single_gpu": ok, "approx_bytes_received_per_rank": int(recv),
-                     "note": "same shards, plus one NCCL all-gather of g / CSR values so that every rank holds the whole "
-                             "Jacobian (north_star); NVLink-bound"}
+        allgather_nccl = {"value": world * 1e3 / ms_g, "unit": UNIT, "ms_per_step": ms_g, "steps": ng, "mode": gather.mode,
+                          "equals_single_gpu": ok, "bytes_received_per_rank": int(recv),
+                          "how": "shard kernel, then one NCCL all-gather of g / CSR values (torch.distributed)"}
 
     # ---- end-to-end: host buffers through the C ABI (pinned); H2D of this rank's z / p and D2H of the rows it owns
     #      inside the timing.  Every rank uses its own PCIe link; no rank waits for another inside the timed region.
@@ -364,6 +396,7 @@ def run_cuda(args):
     }
     if allgather is not None:
         line["allgather"] = allgather
+        line["allgather_nccl"] = allgather_nccl
     if cb is not None:
         line["cpu_baseline"] = cb
     print(json.dumps(line))

@@ -140,6 +140,20 @@ int mpx_eval_g_jac_dev(mpx_plan* plan, const double* d_z, const double* d_p, dou
                        void* stream);
 int mpx_sync(mpx_plan* plan);
 
+/* -- fused evaluation + all-gather over peer memory (multi-GPU, one process per GPU): every store of the g + jac_g
+ *    kernel is issued to this GPU's buffers AND to the same offsets of n_peers peer buffers (other GPUs' allocations
+ *    mapped through CUDA IPC, reached over NVLink), so that once all ranks have evaluated their shard every rank
+ *    holds the whole g / Jacobian -- the all-gather of BASELINE.json's north_star without a separate collective.
+ *    Buffers that peers write into must come from mpx_peer_alloc (cudaMalloc + IPC handle); the 64-byte handle is
+ *    sent to the peers (any transport), which map it with mpx_peer_open. The caller orders the ranks before reading. */
+typedef struct mpx_ipc_handle { unsigned char bytes[64]; } mpx_ipc_handle;
+int mpx_peer_alloc(int32_t device, int64_t bytes, void** dptr, mpx_ipc_handle* handle);
+int mpx_peer_open(int32_t device, const mpx_ipc_handle* handle, void** dptr);
+int mpx_peer_close(void* dptr);
+int mpx_peer_free(void* dptr);
+int mpx_eval_g_jac_dev_peers(mpx_plan* plan, const double* d_z, const double* d_p, double* d_g, double* d_values,
+                             int32_t n_peers, double* const* peer_g, double* const* peer_values, void* stream);
+
 /* -- staged evaluation: ONE upload and ONE fused evaluation per distinct x, results kept in the plan's device
  *    buffers; the pieces are copied out when asked for. This is how the solver-facing shims below honour IPOPT's
  *    new_x flag (eval_g and eval_jac_g of the same x share one kernel launch) and how CasADi's nlp_jac_g gets its

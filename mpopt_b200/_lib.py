@@ -88,6 +88,12 @@ PROTOTYPES = {
                                        C.POINTER(C.c_int), c_f64p, C.c_void_p]),
     "mpx_casadi_bind": (C.c_int, [C.c_void_p]),
     "mpx_sync": (C.c_int, [C.c_void_p]),
+    "mpx_peer_alloc": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),
+    "mpx_peer_open": (C.c_int, [C.c_int32, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mpx_peer_close": (C.c_int, [C.c_void_p]),
+    "mpx_peer_free": (C.c_int, [C.c_void_p]),
+    "mpx_eval_g_jac_dev_peers": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                           C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "mpx_launch_count": (C.c_int64, [C.c_void_p]),
     "mpx_program_origin": (C.c_char_p, [C.c_void_p]),
 }

@@ -199,6 +199,7 @@ struct mpx_plan {
   const void* rt_spec = nullptr;   // RtSpec*: run-time compiled degree-specialised kernels
   std::vector<double> h_p_cache;
   bool p_valid = false;
+  std::vector<int64_t> h_tail_runs[2];  // rows of the small tail kernels (mpx_eval_g_jac_dev_peers)
   std::vector<int64_t> h_runs[3];  // shard plans: (offset, count) runs of g / values / grad_f written by this shard
   int staged = 0;                  // MPX_STAGE_* results currently valid in the device buffers (mpx_stage / mpx_fetch)
   DevBuf d_ccs_perm, d_ccs_vals;   // CCS order of the Jacobian values, built on first use
@@ -1478,6 +1479,94 @@ extern "C" int mpx_eval_g_jac_dev(mpx_plan* p, const double* d_z, const double* 
                                   void* stream) {
   if (!p || !d_z || !d_p || !d_g) return fail(MPX_EINVAL, "NULL argument");
   return launch_g_jac(*p, d_z, d_p, d_g, d_values, stream ? (cudaStream_t)stream : p->stream);
+}
+
+// ------------------------------------------------------------------ fused evaluation + all-gather over peer memory
+// Every store of the g + jac_g kernel is issued once per destination: this GPU's buffers and the same offsets of each
+// peer's buffers (device pointers of other GPUs' allocations, opened through CUDA IPC and reached over NVLink).  When
+// all ranks have run their shard this way every rank holds the whole g / Jacobian without a separate collective;
+// the caller orders the ranks (a barrier or a tiny all-reduce) before it reads.
+extern "C" int mpx_peer_alloc(int32_t device, int64_t bytes, void** dptr, mpx_ipc_handle* handle) {
+  if (!dptr || !handle || bytes <= 0) return fail(MPX_EINVAL, "bad mpx_peer_alloc arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(mpx_ipc_handle), "mpx_ipc_handle too small");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaMalloc(dptr, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, *dptr));
+  memset(handle, 0, sizeof *handle);
+  memcpy(handle, &h, sizeof h);
+  return MPX_OK;
+}
+extern "C" int mpx_peer_open(int32_t device, const mpx_ipc_handle* handle, void** dptr) {
+  if (!dptr || !handle) return fail(MPX_EINVAL, "bad mpx_peer_open arguments");
+  CUDA_TRY(cudaSetDevice(device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof h);
+  CUDA_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MPX_OK;
+}
+extern "C" int mpx_peer_close(void* dptr) {
+  if (dptr) CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+  return MPX_OK;
+}
+extern "C" int mpx_peer_free(void* dptr) {
+  if (dptr) CUDA_TRY(cudaFree(dptr));
+  return MPX_OK;
+}
+
+extern "C" int mpx_eval_g_jac_dev_peers(mpx_plan* p, const double* d_z, const double* d_p, double* d_g, double* d_values,
+                                        int32_t n_peers, double* const* peer_g, double* const* peer_values, void* stream) {
+  if (!p || !d_z || !d_p || !d_g || !d_values) return fail(MPX_EINVAL, "NULL device pointer");
+  if (n_peers < 0 || n_peers > MPX_MAX_PEERS || (n_peers && (!peer_g || !peer_values)))
+    return fail(MPX_EINVAL, "n_peers must be in [0, 7] with both pointer arrays given");
+  if (p->v4 || p->v2_warps == 0 || !p->gather.empty())
+    return fail(MPX_ELIMIT, "peer stores need the default g + jac kernel and an unmasked Jacobian pattern");
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : p->stream;
+  for (auto& a : p->args) {
+    a.n_peers = n_peers;
+    for (int r = 0; r < n_peers; ++r) a.peer_g[r] = peer_g[r], a.peer_vals[r] = peer_values[r];
+  }
+  int rc = launch_g_jac(*p, d_z, d_p, d_g, d_values, st);
+  for (auto& a : p->args) a.n_peers = 0;
+  if (rc) return rc;
+  // rows written by the small tail kernels (slope continuity, phase links): a few values, copied peer by peer
+  bool tails = !p->links.empty() && p->seg_end == p->K;
+  for (auto& L : p->ph) tails |= L.has_dU;
+  if (tails && n_peers) {
+    for (int kind = 0; kind < 2; ++kind) {
+      std::vector<int64_t>& runs = p->h_tail_runs[kind];
+      if (runs.empty()) {
+        const int kb = p->seg_begin, ke = std::min(p->seg_end, p->K - 1);
+        for (auto& L : p->ph)
+          if (L.has_dU && ke > kb)
+            for (int c = 0; c < p->nu; ++c) {
+              if (kind == 0) runs.push_back(L.gdU + (int64_t)c * (p->K - 1) + kb), runs.push_back(ke - kb);
+              else {
+                int64_t sb = 0, se = 0;
+                for (int k = 0; k < ke; ++k) {
+                  const int64_t ss = p->po[k] + p->po[k + 1] + 1;
+                  if (k < kb) sb += ss;
+                  se += ss;
+                }
+                runs.push_back(L.vdU + (int64_t)c * p->nnzS + sb), runs.push_back(se - sb);
+              }
+            }
+        if (!p->links.empty() && p->seg_end == p->K) {
+          if (kind == 0) runs.push_back(p->g_events), runs.push_back(p->n_g - p->g_events);
+          else runs.push_back(p->v_events), runs.push_back(p->nnz_full - p->v_events);
+        }
+        if (runs.empty()) runs.push_back(0), runs.push_back(0);
+      }
+      for (size_t i = 0; i + 1 < runs.size(); i += 2)
+        for (int r = 0; r < n_peers && runs[i + 1] > 0; ++r) {
+          double* dst = (kind == 0 ? peer_g[r] : peer_values[r]) + runs[i];
+          const double* src = (kind == 0 ? d_g : d_values) + runs[i];
+          CUDA_TRY(cudaMemcpyAsync(dst, src, (size_t)runs[i + 1] * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+  }
+  return MPX_OK;
 }
 
 extern "C" int mpx_eval_f_grad_dev(mpx_plan* p, const double* d_z, const double* d_p, double* d_f, double* d_grad,

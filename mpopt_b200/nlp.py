@@ -161,6 +161,14 @@ class Transcription:
     def g_jac_dev(self, z_ptr, p_ptr, g_ptr, vals_ptr, stream=None):
         _lib.check(self._L.mpx_eval_g_jac_dev(self._plan, z_ptr, p_ptr, g_ptr, vals_ptr, stream))
 
+    def g_jac_dev_peers(self, z_ptr, p_ptr, g_ptr, vals_ptr, peer_g, peer_vals, stream=None):
+        """Fused evaluation + all-gather: every store also goes to the peers' buffers (device pointers obtained with
+        ``mpopt_b200.shard.PeerBuffers``)."""
+        n = len(peer_g)
+        pg = (C.c_void_p * max(n, 1))(*peer_g)
+        pv = (C.c_void_p * max(n, 1))(*peer_vals)
+        _lib.check(self._L.mpx_eval_g_jac_dev_peers(self._plan, z_ptr, p_ptr, g_ptr, vals_ptr, n, pg, pv, stream))
+
     def f_grad_dev(self, z_ptr, p_ptr, f_ptr, grad_ptr, stream=None):
         _lib.check(self._L.mpx_eval_f_grad_dev(self._plan, z_ptr, p_ptr, f_ptr, grad_ptr, stream))
 

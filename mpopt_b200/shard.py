@@ -148,3 +148,75 @@ class Gatherer:
             self._inplace(g, vals)
         else:
             self._packed(g, vals)
+
+
+class _DevArray:
+    """A device allocation seen through ``__cuda_array_interface__`` (lets torch view memory it did not allocate)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+
+class PeerBuffers:
+    """Output buffers every rank can write into: the fused evaluation + all-gather of the north-star path.
+
+    Each rank allocates ``n_sets`` pairs (g, values) with ``mpx_peer_alloc`` (cudaMalloc + CUDA IPC handle), the
+    handles are exchanged through ``dist.all_gather_object`` and mapped with ``mpx_peer_open``; ``local(k)`` gives this
+    rank's tensors of set ``k`` and ``peers(k)`` the device pointers of the same set on the other ranks, in the form
+    ``Transcription.g_jac_dev_peers`` takes.  One process per GPU, all GPUs on one node (NVLink / NVSwitch)."""
+
+    def __init__(self, n_g, nnz, dist, rank, device_index, n_sets=1):
+        import ctypes as C
+
+        import torch
+
+        from . import _lib
+
+        L = _lib.lib()
+        self._L, self.dist, self.rank, self.world = L, dist, rank, dist.get_world_size()
+        self._own, self._opened, self._tensors = [], [], []
+        handles = []
+        for _ in range(n_sets):
+            pair = []
+            for n in (n_g, nnz):
+                ptr, h = C.c_void_p(), (C.c_ubyte * 64)()
+                _lib.check(L.mpx_peer_alloc(device_index, 8 * n, C.byref(ptr), h))
+                self._own.append(ptr.value)
+                pair.append((ptr.value, bytes(h)))
+            handles.append([hb for _, hb in pair])
+            self._tensors.append(tuple(torch.as_tensor(_DevArray(pv, n), device=torch.device("cuda", device_index))
+                                       for (pv, _), n in zip(pair, (n_g, nnz))))
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles)
+        self._peer_ptrs = []  # [set] -> ([g pointers of the other ranks], [values pointers of the other ranks])
+        for k in range(n_sets):
+            pg, pv = [], []
+            for r in range(self.world):
+                if r == rank:
+                    continue
+                for which, dstl in ((0, pg), (1, pv)):
+                    ptr = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(everyone[r][k][which])
+                    _lib.check(L.mpx_peer_open(device_index, hb, C.byref(ptr)))
+                    self._opened.append(ptr.value)
+                    dstl.append(ptr.value)
+            self._peer_ptrs.append((pg, pv))
+
+    def local(self, k):
+        return self._tensors[k]
+
+    def peers(self, k):
+        return self._peer_ptrs[k]
+
+    def close(self):
+        import torch
+
+        torch.cuda.synchronize()
+        self.dist.barrier()  # nobody is still writing into anybody's buffers
+        for p in self._opened:
+            self._L.mpx_peer_close(p)
+        self._tensors = []
+        self.dist.barrier()
+        for p in self._own:
+            self._L.mpx_peer_free(p)
+        self._opened, self._own = [], []

@@ -210,3 +210,39 @@ def test_unregistered_problem_compiles_at_run_time(libmpx):
     assert_close(tr.grad_f(z, p), ora.grad_f(z, p), "grad_f (nvrtc)")
     tr2 = Transcription(ocp, 3, 5, "CGL")  # second plan of the same program: served from the in-process cache
     assert tr2.program_origin == tr.program_origin.split(";")[0] + ";" + tr2.program_origin.split(";")[1]
+
+
+@pytest.mark.gpu
+def test_peer_stores_replicate_every_output():
+    """mpx_eval_g_jac_dev_peers (fused evaluation + all-gather): every g / Jacobian value also lands in the peers'
+    buffers.  One GPU is enough to check the replication: the 'peers' are two more buffer pairs on the same device;
+    a shard plan must leave the rows of other shards untouched."""
+    import torch
+
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import kitchen_sink, synthetic_6_3
+
+    for make, K, p, seg in ((synthetic_6_3, 12, 15, (4, 9)), (synthetic_6_3, 7, 4, None), (kitchen_sink, 6, 5, (2, 6))):
+        ocp = make()
+        tr = Transcription(ocp, K, p, "LGR", drop_exact_zeros=False, segments=seg)
+        rng = np.random.default_rng(3)
+        z = rng.uniform(-1, 1, tr.n_z)
+        for ph in range(tr.P):
+            z[(ph + 1) * (tr.n_z // tr.P) - 2 - tr.na] = 0.5 * ph
+            z[(ph + 1) * (tr.n_z // tr.P) - 1 - tr.na] = 2.0 + ph
+        w = np.concatenate([rng.dirichlet(np.ones(K)) for _ in range(tr.P)])
+        dev = torch.device("cuda", 0)
+        zd, wd = torch.from_numpy(z).to(dev), torch.from_numpy(w).to(dev)
+        mk = lambda n: torch.full((n,), -7.0, dtype=torch.float64, device=dev)
+        g0, v0 = mk(tr.n_g), mk(tr.nnz)
+        tr.g_jac_dev(zd.data_ptr(), wd.data_ptr(), g0.data_ptr(), v0.data_ptr())
+        tr.sync()
+        g1, v1, g2, v2, g3, v3 = mk(tr.n_g), mk(tr.nnz), mk(tr.n_g), mk(tr.nnz), mk(tr.n_g), mk(tr.nnz)
+        tr.g_jac_dev_peers(zd.data_ptr(), wd.data_ptr(), g1.data_ptr(), v1.data_ptr(), [g2.data_ptr(), g3.data_ptr()],
+                           [v2.data_ptr(), v3.data_ptr()])
+        tr.sync()
+        torch.cuda.synchronize()
+        for a, b in ((g1, g0), (g2, g0), (g3, g0), (v1, v0), (v2, v0), (v3, v0)):
+            assert torch.equal(a, b)
+        if seg is not None:  # rows of the other shards were not written
+            assert (g0 == -7.0).any() and (v0 == -7.0).any()
