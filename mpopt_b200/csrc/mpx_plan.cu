@@ -362,7 +362,8 @@ RtApi& rt_api() {
   if (tried) return api;
   tried = true;
   void* hn = nullptr;
-  for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12"})
+  // the toolkit's own NVRTC first (same release as the nvcc that built the AOT instances), then whatever the loader finds
+  for (const char* n : {"/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so.12", "libnvrtc.so"})
     if ((hn = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
   void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
   if (!hn || !hc) {

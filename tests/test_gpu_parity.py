@@ -179,6 +179,102 @@ def test_headline_counts(libmpx):
     assert_close(g, ora.g(z, p), "headline g")
 
 
+def _full_size_against_oracle(make, K, po, scheme, counts, tf):
+    """Whole problem against the oracle (structure bit-exact, values 1e-10); the oracle gets the device's tables, which
+    the table tests hold to <= 1e-11 of its own, so that exact-zero folding picks the same entries."""
+    from mpopt_b200.nlp import Transcription
+    from oracle.nlp import OracleNLP
+
+    tr = Transcription(make(), K, po, scheme)
+    assert (tr.n_z, tr.n_g, tr.nnz) == counts
+    degs = sorted(set(po)) if isinstance(po, list) else [po]
+    ora = OracleNLP(make(), K, po, scheme, tables={d: tr.tables(d) for d in degs})
+    z, p = random_point(ora, tf=tf, dirichlet=True)
+    J = ora.jac_g(z, p)
+    rp, ci = tr.structure()
+    assert np.array_equal(rp, J.indptr) and np.array_equal(ci, J.indices)
+    g = np.empty(tr.n_g)
+    assert_close(tr.jac_g_values(z, p, g_out=g), J.data, "jac_g values")
+    assert_close(g, ora.g(z, p), "g")
+    assert_close(tr.f(z, p), ora.f(z, p), "f")
+    assert_close(tr.grad_f(z, p), ora.grad_f(z, p), "grad_f")
+    return tr
+
+
+def test_config3_full_size(libmpx):
+    """BASELINE config 3: van-der-Pol, 2048 segments of mixed degree [3, 30, 3, ...], CGL."""
+    from mpopt_b200.problems import van_der_pol
+
+    po = [30 if k % 3 == 1 else 3 for k in range(2048)]
+    tr = _full_size_against_oracle(van_der_pol, 2048, po, "CGL", (73760, 73757, 2126820), 10.0)
+    assert "gjac=v2" in tr.program_origin and "/d" not in tr.program_origin  # mixed degrees: generic instance
+
+
+def test_config4_full_size(libmpx):
+    """BASELINE config 4: synthetic 6/3, 8192 segments of degree 20, LGL (odd block offsets: thread-store fallback)."""
+    from mpopt_b200.problems import synthetic_6_3
+
+    tr = _full_size_against_oracle(synthetic_6_3, 8192, 20, "LGL", (1474571, 1474566, 40796346), 1.0)
+    assert tr.program_origin.endswith("gjac=v2/d20")
+
+
+def test_config5_full_size(libmpx):
+    """BASELINE config 5 stand-in: two-phase Schwartz, 1024 segments per phase, degree 10, LGR."""
+    from mpopt_b200.problems import two_phase_schwartz
+
+    from mpopt_b200.nlp import Transcription
+    from oracle.nlp import OracleNLP
+
+    tr = Transcription(two_phase_schwartz(), 1024, 10, "LGR")
+    ora = OracleNLP(two_phase_schwartz(), 1024, 10, "LGR", tables={10: tr.tables(10)})
+    assert (tr.n_z, tr.n_g, tr.nnz) == (ora.n_z, ora.n_g, ora.jac_g(*random_point(ora)).nnz)
+    z, p = random_point(ora, dirichlet=True)
+    J = ora.jac_g(z, p)
+    rp, ci = tr.structure()
+    assert np.array_equal(rp, J.indptr) and np.array_equal(ci, J.indices)
+    g = np.empty(tr.n_g)
+    assert_close(tr.jac_g_values(z, p, g_out=g), J.data, "jac_g values")
+    assert_close(g, ora.g(z, p), "g")
+    assert tr.program_origin.endswith("gjac=v2/d10")
+
+
+@pytest.mark.parametrize("env", [{"MPX_JIT": "1"}, {"MPX_NOSPEC": "1"}, {"MPX_KERNEL": "v4"}, {"MPX_KERNEL": "v4", "MPX_NOSPEC": "1"},
+                                 {"MPX_KERNEL": "v1"}, {"MPX_CONST_FIRST": "0", "MPX_V2_NBUF": "1", "MPX_PDL": "0"}])
+def test_kernel_variants_agree(libmpx, monkeypatch, env):
+    """Every g + jac_g kernel variant (degree-specialised AOT / NVRTC / generic v2, row-block teams v4, CTA-per-segment
+    v1, and v2 with its scheduling features off) agrees with the default on the same inputs to 1e-13."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import kitchen_sink, synthetic_6_3
+
+    for make, K, po in ((synthetic_6_3, 40, 15), (kitchen_sink, 9, 6), (synthetic_6_3, 11, 4)):
+        ref = Transcription(make(), K, po, "LGR")
+        rng = np.random.default_rng(11)
+        z = rng.uniform(-1, 1, ref.n_z)
+        nvar = ref.n_z // ref.P
+        for ph in range(ref.P):
+            z[(ph + 1) * nvar - 2 - ref.na] = 0.3 * ph
+            z[(ph + 1) * nvar - 1 - ref.na] = 1.5 + ph
+        w = np.concatenate([rng.dirichlet(np.ones(K)) for _ in range(ref.P)])
+        g0 = np.empty(ref.n_g)
+        v0 = ref.jac_g_values(z, w, g_out=g0)
+        go0 = ref.g(z, w)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        tr = Transcription(make(), K, po, "LGR")
+        for k in env:
+            monkeypatch.delenv(k)
+        if env.get("MPX_JIT") == "1" and "/d" not in ref.program_origin:
+            assert "/jit-d" in tr.program_origin
+        if env.get("MPX_KERNEL") in ("v4", "v1"):
+            assert "gjac=" + env["MPX_KERNEL"] in tr.program_origin
+        g1 = np.empty(tr.n_g)
+        v1 = tr.jac_g_values(z, w, g_out=g1)
+        # different instances may contract a*b+c differently: a few ulp, far inside the 1e-10 parity tolerance
+        assert_close(v1, v0, f"values {env} {tr.program_origin}", 1e-13)
+        assert_close(g1, g0, f"g {env} {tr.program_origin}", 1e-13)
+        assert_close(tr.g(z, w), go0, f"g-only {env}", 1e-13)
+
+
 def test_unregistered_problem_compiles_at_run_time(libmpx):
     """A problem that is not in problems.REGISTRY: its functors are compiled through NVRTC from the same kernel
     header, and the result has the same parity with the oracle."""
@@ -220,9 +316,9 @@ def test_peer_stores_replicate_every_output():
     import torch
 
     from mpopt_b200.nlp import Transcription
-    from mpopt_b200.problems import kitchen_sink, synthetic_6_3
+    from mpopt_b200.problems import synthetic_6_3, two_phase_schwartz
 
-    for make, K, p, seg in ((synthetic_6_3, 12, 15, (4, 9)), (synthetic_6_3, 7, 4, None), (kitchen_sink, 6, 5, (2, 6))):
+    for make, K, p, seg in ((synthetic_6_3, 12, 15, (4, 9)), (synthetic_6_3, 7, 4, None), (two_phase_schwartz, 6, 5, (2, 6))):
         ocp = make()
         tr = Transcription(ocp, K, p, "LGR", drop_exact_zeros=False, segments=seg)
         rng = np.random.default_rng(3)
