@@ -154,6 +154,16 @@ int mpx_peer_free(void* dptr);
 int mpx_eval_g_jac_dev_peers(mpx_plan* plan, const double* d_z, const double* d_p, double* d_g, double* d_values,
                              int32_t n_peers, double* const* peer_g, double* const* peer_values, void* stream);
 
+/* -- interpolation of a solution and the dynamics residual at arbitrary points: replaces, per phase,
+ *    mpopt.interpolate_single_phase + get_dynamics_residuals_single_phase (mpopt.py:1428-1542), the step after every
+ *    solve (process_results) and the inner loop of mpopt_h_adaptive. Point i lies in segment seg[i] at the local
+ *    abscissa taus[i] in [tau_min, tau_max] (the reference's per-segment tau lists, flattened). Outputs, any of which
+ *    may be NULL, row-major: xi[n][nx], ui[n][nu] (interpolated, scaled variables), ti[n] (time), dxi[n][nx],
+ *    dui[n][nu] (d/dtau through the segment's Lagrange basis), res[n][nx] = dxi - h_seg Sx f(xi/Sx, ui/Su, ti, a/Sa). */
+int mpx_eval_residuals(mpx_plan* plan, const double* z, const double* p, int32_t phase, int64_t n_points,
+                       const int32_t* seg, const double* taus, double* xi, double* ui, double* ti, double* dxi,
+                       double* dui, double* res);
+
 /* -- staged evaluation: ONE upload and ONE fused evaluation per distinct x, results kept in the plan's device
  *    buffers; the pieces are copied out when asked for. This is how the solver-facing shims below honour IPOPT's
  *    new_x flag (eval_g and eval_jac_g of the same x share one kernel launch) and how CasADi's nlp_jac_g gets its

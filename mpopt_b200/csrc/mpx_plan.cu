@@ -390,7 +390,7 @@ RtApi& rt_api() {
 // launches through the driver API; same interface as the AOT phases
 struct MpxRtPhase final : MpxPhaseKernels {
   CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_gjac4[2] = {nullptr, nullptr},
-               f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr};
+               f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr}, f_resid[2] = {nullptr, nullptr};
   static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st,
                         bool pdl = false) {
     RtApi& R = rt_api();
@@ -430,6 +430,9 @@ struct MpxRtPhase final : MpxPhaseKernels {
   cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const override {
     return go(f_final[grad], a, 1, 256, 0, st);
   }
+  cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const override {
+    return go(f_resid[deriv], a, grid, 128, 0, st);
+  }
 };
 
 struct RtProgram {
@@ -466,7 +469,8 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   if (R.CreateProgram(&prog, src.c_str(), "mpx_rt.cu", 0, nullptr, nullptr) != 0) return fail(MPX_ECUDA, "nvrtcCreateProgram failed");
   std::vector<std::string> names;
   for (int ph = 0; ph < n_phases; ++ph)
-    for (const char* k : {"mpx_gjac_kernel", "mpx_gjac2_kernel", "mpx_gjac4_kernel", "mpx_fgrad_kernel", "mpx_fgrad_final"})
+    for (const char* k : {"mpx_gjac_kernel", "mpx_gjac2_kernel", "mpx_gjac4_kernel", "mpx_fgrad_kernel", "mpx_fgrad_final",
+                          "mpx_residual_kernel"})
       for (const char* b : {"false", "true"})
         names.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ", " + b +
                         (strcmp(k, "mpx_gjac4_kernel") == 0 || strcmp(k, "mpx_gjac2_kernel") == 0 ? ", 0>" : ">"));
@@ -496,8 +500,8 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   size_t idx = 0;
   for (int ph = 0; ph < n_phases; ++ph) {
     std::unique_ptr<MpxRtPhase> P(new MpxRtPhase());
-    CUfunction_t* slots[5] = {P->f_gjac, P->f_gjac2, P->f_gjac4, P->f_fgrad, P->f_final};
-    for (int k = 0; k < 5; ++k)
+    CUfunction_t* slots[6] = {P->f_gjac, P->f_gjac2, P->f_gjac4, P->f_fgrad, P->f_final, P->f_resid};
+    for (int k = 0; k < 6; ++k)
       for (int b = 0; b < 2; ++b, ++idx) {
         const char* lowered = nullptr;
         if (R.GetLoweredName(prog, names[idx].c_str(), &lowered) != 0 || !lowered ||
@@ -1415,6 +1419,55 @@ extern "C" int mpx_eval_grad_f(mpx_plan* p, const double* z, const double* pw, d
   if (rc) return rc;
   if (f) CUDA_TRY(cudaMemcpyAsync(f, p->d_f.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaMemcpyAsync(grad, p->d_grad.p, (size_t)p->n_z * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+// ------------------------------------------------------------------ interpolation / dynamics residual at arbitrary points
+extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw, int32_t phase, int64_t n_points,
+                                  const int32_t* seg, const double* taus, double* xi, double* ui, double* ti, double* dxi,
+                                  double* dui, double* res) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  if (phase < 0 || phase >= p->P) return fail(MPX_EINVAL, "phase out of range");
+  if (n_points < 0 || (n_points && (!seg || !taus))) return fail(MPX_EINVAL, "bad point list");
+  if (p->seg_begin != 0 || p->seg_end != p->K) return fail(MPX_EINVAL, "residuals need a plan over all segments");
+  for (int64_t i = 0; i < n_points; ++i)
+    if (seg[i] < 0 || seg[i] >= p->K) return fail(MPX_EINVAL, "segment index out of range in the point list");
+  int rc = upload_inputs(*p, z, pw);
+  if (rc || n_points == 0) return rc;
+  const int nx = p->nx, nu = p->nu;
+  const bool deriv = dxi || dui || res;
+  DevBuf dseg, dtau, dout;
+  const size_t per = (size_t)(2 * nx + 2 * nu + 1 + nx);
+  CUDA_TRY(dseg.ensure((size_t)n_points * sizeof(int32_t)));
+  CUDA_TRY(dtau.ensure((size_t)n_points * sizeof(double)));
+  CUDA_TRY(dout.ensure((size_t)n_points * per * sizeof(double)));
+  CUDA_TRY(cudaMemcpyAsync(dseg.p, seg, (size_t)n_points * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream));
+  CUDA_TRY(cudaMemcpyAsync(dtau.p, taus, (size_t)n_points * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  mpx_scan_widths_kernel<<<p->P, 32, 0, p->stream>>>(p->d_p.as<double>(), p->d_sig0.as<double>(), p->K);
+  ++p->launches;
+  MpxPhaseArgs a = p->args[phase];
+  a.z = p->d_z.as<double>(), a.w = p->d_p.as<double>() + (int64_t)phase * p->K;
+  a.sig0 = p->d_sig0.as<double>() + (int64_t)phase * p->K;
+  a.pt_seg = dseg.as<int32_t>(), a.pt_tau = dtau.as<double>(), a.n_points = n_points;
+  double* o = dout.as<double>();
+  a.r_xi = o, o += n_points * nx;
+  a.r_ui = o, o += n_points * nu;
+  a.r_ti = o, o += n_points;
+  a.r_dxi = o, o += n_points * nx;
+  a.r_dui = o, o += n_points * nu;
+  a.r_res = o;
+  CUDA_TRY(p->prog->phases[phase]->residual(a, deriv, (int)((n_points + 127) / 128), p->stream));
+  ++p->launches;
+  auto back = [&](double* dst, const double* src, size_t n) -> cudaError_t {
+    return dst && n ? cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, p->stream) : cudaSuccess;
+  };
+  CUDA_TRY(back(xi, a.r_xi, (size_t)n_points * nx));
+  CUDA_TRY(back(ui, a.r_ui, (size_t)n_points * nu));
+  CUDA_TRY(back(ti, a.r_ti, (size_t)n_points));
+  CUDA_TRY(back(dxi, a.r_dxi, (size_t)n_points * nx));
+  CUDA_TRY(back(dui, a.r_dui, (size_t)n_points * nu));
+  CUDA_TRY(back(res, a.r_res, (size_t)n_points * nx));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;
 }

@@ -21,6 +21,7 @@ struct MpxPhaseKernels {
   virtual bool has_degree(int deg) const = 0;
   virtual cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const = 0;
+  virtual cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const = 0;
 };
 
 struct MpxProgramEntry {
@@ -135,6 +136,11 @@ struct MpxAotPhase final : MpxPhaseKernels {
   cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const override {
     if (grad) mpx_fgrad_final<PH, true><<<1, 256, 0, st>>>(a);
     else mpx_fgrad_final<PH, false><<<1, 256, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const override {
+    if (deriv) mpx_residual_kernel<PH, true><<<grid, 128, 0, st>>>(a);
+    else mpx_residual_kernel<PH, false><<<grid, 128, 0, st>>>(a);
     return cudaGetLastError();
   }
 };

@@ -63,36 +63,6 @@ __host__ __device__ double mpx_jacobi_root(int n, int j, double al, double be) {
   return x;
 }
 
-// l_j(tau) on nodes R[0..n1)
-__host__ __device__ __forceinline__ double mpx_lagrange(const double* R, int n1, int j, double tau) {
-  double v = 1.0;
-  for (int i = 0; i < n1; ++i)
-    if (i != j) v *= (tau - R[i]) / (R[j] - R[i]);
-  return v;
-}
-// d^order l_j / dtau^order at an arbitrary point: term-by-term derivative of the product form
-__host__ __device__ double mpx_lagrange_der(const double* R, int n1, int j, double tau, int order) {
-  double sum = 0.0;
-  for (int k = 0; k < n1; ++k) {
-    if (k == j) continue;
-    if (order == 1) {
-      double term = 1.0 / (R[j] - R[k]);
-      for (int i = 0; i < n1; ++i)
-        if (i != j && i != k) term *= (tau - R[i]) / (R[j] - R[i]);
-      sum += term;
-    } else {
-      for (int l = 0; l < n1; ++l) {
-        if (l == j || l == k) continue;
-        double term = 1.0 / ((R[j] - R[k]) * (R[j] - R[l]));
-        for (int i = 0; i < n1; ++i)
-          if (i != j && i != k && i != l) term *= (tau - R[i]) / (R[j] - R[i]);
-        sum += term;
-      }
-    }
-  }
-  return sum;
-}
-
 // nodes of one degree into shared memory R[n1] (mapped to [tmin, tmax]); all threads of the CTA call it
 __device__ void mpx_nodes(int scheme, int d, double tmin, double tmax, double* R) {
   const int n1 = d + 1;

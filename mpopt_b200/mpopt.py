@@ -8,8 +8,10 @@ nlp_bounds, nlp_solver, _nlp_sw_params``) and the methods of the reference's ``c
 ``get_event_constraints``.  What CasADi built symbolically there is a ``Transcription`` here: the user's Python
 callables are traced once and the four NLP evaluators run as CUDA kernels.
 
-Out of scope: the adaptive subclasses, residual post-processing and plotting.
-``process_results`` returns a light object with ``get_data`` / ``get_trajectories`` only.
+Also here, from the "next" rows of SURVEY.md section 8f: the interpolation / dynamics-residual path
+(``get_residual_grid_taus``, ``interpolate_single_phase``, ``get_dynamics_residuals*``, evaluated on the GPU).
+Out of scope: the adaptive subclasses and plotting; ``process_results`` returns a light object with ``get_data`` /
+``get_trajectories`` only.
 """
 from __future__ import annotations
 
@@ -167,6 +169,95 @@ class mpopt:
             print(f" \t OCP transcription time  : {round((t1 - t0) * 1e3, 3)} ms")
             print(f" \t NLP solution time       : {round((t2 - t1) * 1e3, 3)} ms")
         return solution
+
+    # ------------------------------------------------------------------ interpolation / residuals (mpopt.py:1152-1573)
+    @staticmethod
+    def compute_interpolation_taus_corresponding_to_original_grid(nodes_req, seg_widths, tau0=0, tau1=1):
+        """Global target nodes -> per-segment local taus (mpopt.py:1205-1237): a node on a segment boundary belongs to
+        the earlier segment, the first node to nobody."""
+        nodes_req = np.asarray(nodes_req, dtype=float)
+        csw = np.append(0, np.cumsum(seg_widths))
+        assert abs(csw[-1] - 1) < 1e-6
+        scaled = 0 + (1 - 0) / (tau1 - tau0) * (nodes_req - tau0)
+        taus = [None] * len(seg_widths)
+        for i, seg in enumerate(seg_widths):
+            t = scaled[scaled > csw[i]]
+            t = t[t <= csw[i + 1]]
+            taus[i] = tau0 + (tau1 - tau0) / (1 - 0) * ((t - csw[i]) / seg - 0)
+        return taus
+
+    @staticmethod
+    def get_interpolated_time_grid(t_orig, taus, poly_orders, tau0, tau1):
+        """mpopt.py:1544-1573 (returns a column, like the reference's DM)."""
+        t_orig = np.asarray(t_orig, dtype=float).reshape(-1)
+        t_seg = [t_orig[0]] + [t_orig[sum(poly_orders[: i + 1])] for i in range(len(poly_orders))]
+        grid = [t_seg[i] + (t_seg[i + 1] - t_seg[i]) * (0 + (1 - 0) / (tau1 - tau0) * (np.asarray(taus[i], float) - tau0))
+                for i in range(len(t_seg) - 1)]
+        return np.concatenate(grid).reshape(-1, 1)
+
+    def get_residual_grid_taus(self, phase: int = 0, grid_type: str = None):
+        """Non-collocation points per segment: "fixed", "mid-points", "spectral" (mpopt.py:1152-1203)."""
+        if not self._collocation_approximation_computed:
+            self.compute_numerical_approximation()
+        if grid_type is None:
+            grid_type = self.grid_type[phase]
+        sw = np.asarray(getattr(self, "_nlp_sw_params", self.get_segment_width_parameters()), dtype=float)
+        if grid_type == "fixed":
+            n_nodes = max(sum(self.poly_orders) + 2, self._MAX_GRID_POINTS + 2)
+            target = np.linspace(self.tau0, self.tau1, n_nodes)
+            taus = self.compute_interpolation_taus_corresponding_to_original_grid(
+                target, sw[self.n_segments * phase: self.n_segments * (phase + 1)], tau0=self.tau0, tau1=self.tau1)
+            taus[0] = taus[0][:-1]
+            return taus
+        if grid_type == "mid-points":
+            return [(np.asarray(self.collocation._taus_fn(d))[:-1] + np.asarray(self.collocation._taus_fn(d))[1:]) / 2.0
+                    for d in self.poly_orders]
+        if grid_type == "spectral":
+            return [np.array(self.collocation._taus_fn(self._MAX_GRID_POINTS + 2)[1:-1]) for _ in self.poly_orders]
+        return None
+
+    def interpolate_single_phase(self, solution, phase: int = 0, target_nodes=None, grid_type=None, options={}):
+        """(Xi, Ui, ti, a, DXi, DUi, target_nodes, t0, tf) at per-segment taus, evaluated on the GPU (mpopt.py:1489-1542)."""
+        if target_nodes is None:
+            target_nodes = self.get_residual_grid_taus(phase=phase, grid_type=grid_type)
+        tr, o = self.transcription, self._ocp
+        z = np.asarray(solution["x"], dtype=float).reshape(-1)
+        sw = np.asarray(getattr(self, "_nlp_sw_params", self.get_segment_width_parameters()), dtype=float)
+        r = tr.residuals(z, sw, phase, target_nodes)
+        L = tr.layout
+        a = z[L.colT0(phase) + 2: (phase + 1) * L.nvar]
+        t0, tf = z[L.colT0(phase)] / o.scale_t, z[L.colTF(phase)] / o.scale_t
+        self._last_residuals = r
+        return (r["xi"], r["ui"], r["ti"].reshape(-1, 1), a, r["dxi"], r["dui"], target_nodes, np.atleast_1d(t0),
+                np.atleast_1d(tf))
+
+    def get_dynamics_residuals_single_phase(self, solution, phase: int = 0, target_nodes=None):
+        """(ti, residual, h Sx f) per segment, None / [] for a segment without points (mpopt.py:1428-1487)."""
+        xi, ui, ti, a, dxi, dui, taus, t0, tf = self.interpolate_single_phase(solution, phase, target_nodes)
+        res = self._last_residuals["res"]
+        n = [len(t) for t in taus]
+        off = np.concatenate([[0], np.cumsum(n)]).astype(int)
+        K = self.n_segments
+        res_seg = [res[off[k]: off[k + 1]] if n[k] else None for k in range(K)]
+        dyn_seg = [(dxi - res)[off[k]: off[k + 1]] if n[k] else None for k in range(K)]
+        ti_seg = [ti[off[k]: off[k + 1]] if n[k] else [] for k in range(K)]
+        return ti_seg, res_seg, dyn_seg
+
+    def get_dynamics_residuals(self, solution, nodes=None, grid_type=None, residual_type=None, plot=False, fig=None,
+                               axs=None):
+        """Residual of the dynamics at non-collocation points, per phase and segment (mpopt.py:1360-1426)."""
+        residuals, ti = [None] * self._ocp.n_phases, [None] * self._ocp.n_phases
+        for phase in range(self._ocp.n_phases):
+            target = nodes[phase] if nodes is not None else self.get_residual_grid_taus(
+                phase, grid_type=self.grid_type[phase] if grid_type is None else grid_type)
+            ti[phase], residuals[phase], dyn = self.get_dynamics_residuals_single_phase(solution, phase, target)
+            if residual_type == "relative":
+                mx = np.zeros(self._ocp.nx)
+                for d in dyn:
+                    if d is not None:
+                        mx = np.maximum(mx, np.abs(d).max(axis=0))
+                residuals[phase] = [r / mx if r is not None else None for r in residuals[phase]]
+        return ti, residuals
 
     # ------------------------------------------------------------------ results
     def process_results(self, solution, plot: bool = False, scaling: bool = False, residual_x=False, residual_dx=False):

@@ -157,6 +157,31 @@ class Transcription:
         rp, ci = self.structure()
         return sp.csr_matrix((self.jac_g_values(z, p), ci, rp), shape=(self.n_g, self.n_z))
 
+    # ------------------------------------------------------------------ interpolation / residuals
+    def residuals(self, z, p=None, phase=0, taus=None, derivatives=True):
+        """Interpolate the solution ``z`` and evaluate the dynamics residual at per-segment local abscissae.
+
+        ``taus``: one array per segment (possibly empty) of points in ``[tau_min, tau_max]`` -- the reference's
+        ``target_nodes`` (mpopt.py:1489-1542, :1428-1487).  Returns a dict of arrays whose rows are the points, segment by
+        segment: ``xi`` (n, nx), ``ui`` (n, nu), ``ti`` (n,), and with ``derivatives`` also ``dxi``, ``dui`` and
+        ``res = dxi - h Sx f``; ``counts`` is the number of points per segment."""
+        z, p = self._zp(z, p)
+        if taus is None or len(taus) != self.K:
+            raise ValueError("taus must hold one array per segment")
+        counts = [len(t) for t in taus]
+        n = int(sum(counts))
+        seg = np.repeat(np.arange(self.K, dtype=np.int32), counts)
+        tau = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=float).reshape(-1) for t in taus])
+                                   if n else np.zeros(0))
+        out = {"xi": np.empty((n, self.nx)), "ui": np.empty((n, self.nu)), "ti": np.empty(n), "counts": counts}
+        if derivatives:
+            out.update(dxi=np.empty((n, self.nx)), dui=np.empty((n, self.nu)), res=np.empty((n, self.nx)))
+        ptr = lambda k: _lib.ptr(out[k]) if k in out and out[k].size else None
+        _lib.check(self._L.mpx_eval_residuals(self._plan, _lib.ptr(z), _lib.ptr(p), int(phase), n,
+                                              _lib.ptr(seg, _lib.c_i32p), _lib.ptr(tau), ptr("xi"), ptr("ui"), ptr("ti"),
+                                              ptr("dxi"), ptr("dui"), ptr("res")))
+        return out
+
     # ------------------------------------------------------------------ evaluators (device pointers)
     def g_jac_dev(self, z_ptr, p_ptr, g_ptr, vals_ptr, stream=None):
         _lib.check(self._L.mpx_eval_g_jac_dev(self._plan, z_ptr, p_ptr, g_ptr, vals_ptr, stream))

@@ -342,3 +342,34 @@ def test_peer_stores_replicate_every_output():
             assert torch.equal(a, b)
         if seg is not None:  # rows of the other shards were not written
             assert (g0 == -7.0).any() and (v0 == -7.0).any()
+
+
+@pytest.mark.parametrize("problem,K,po,scheme", [("van_der_pol", 5, [3, 6, 4, 9, 2], "LGR"), ("synthetic_6_3", 4, 15, "LGL"),
+                                                 ("two_phase_schwartz", 3, 7, "CGL"), ("kitchen_sink", 4, [4, 3, 5, 4], "LGR")])
+def test_interpolation_and_residuals_match_oracle(libmpx, problem, K, po, scheme):
+    """interpolation of a solution and the dynamics residual at arbitrary per-segment points
+    (mpx_eval_residuals) against the oracle's restatement of mpopt.py:1428-1542, ragged and empty segments included."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle import residual as R
+    from oracle.nlp import OracleNLP
+
+    tr = Transcription(REGISTRY[problem](), K, po, scheme)
+    ora = OracleNLP(REGISTRY[problem](), K, po, scheme)
+    z, p = random_point(ora, dirichlet=True)
+    rng = np.random.default_rng(2)
+    for ph in range(ora.P):
+        grids = [R.residual_grid_taus(ora, ph, "mid-points", p), R.residual_grid_taus(ora, ph, "fixed", p),
+                 [np.sort(rng.uniform(ora.tau0, ora.tau1, int(rng.integers(0, 6)))) for _ in range(K)],
+                 [np.array([ora.tau0, ora.tau1]) if k % 2 == 0 else np.array([]) for k in range(K)]]
+        for taus in grids:
+            got = tr.residuals(z, p, ph, taus)
+            Xi, Ui, ti, DXi, DUi = R.interpolate_phase(ora, z, p, ph, taus)
+            _, res, _, n = R.dynamics_residuals_phase(ora, z, p, ph, taus)
+            assert got["counts"] == n
+            assert_close(got["xi"], Xi, "Xi")
+            assert_close(got["ui"], Ui, "Ui")
+            assert_close(got["ti"], ti, "ti")
+            assert_close(got["dxi"], DXi, "DXi")
+            assert_close(got["dui"], DUi, "DUi")
+            assert_close(got["res"], res, "residual")
