@@ -179,6 +179,14 @@ def run_cuda(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if world > 1:  # keep each rank (and the pinned host buffers it first-touches) on the CPU cores next to its GPU
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        except Exception:
+            pass
     K = WORKLOAD["n_segments"]
     Kt = K * world  # weak scaling: 4096 segments per GPU
     deg, scheme = WORKLOAD["poly_orders"], WORKLOAD["scheme"]
