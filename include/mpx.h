@@ -63,6 +63,10 @@ typedef struct mpx_phase_desc {
   int32_t midu;            /* mid-point control rows present, mpopt.py:330-377             */
   int32_t du_continuity;   /* slope-continuity rows present (needs n_segments>1), :379-413 */
   int32_t cost_t;          /* running cost depends on t explicitly                         */
+  /* second-derivative patterns for the Hessian of the Lagrangian (may be NULL: then mpx_*hess* fail);
+   * lower triangle used, row-major, variables (x.., u.., a.., t, h) resp. (xf.., x0.., tf, t0, a..) */
+  const uint8_t* pat_hw;   /* [nv+2][nv+2]  node Lagrangian h (sw L - sum lamF Sx f) + sum lamC c     */
+  const uint8_t* pat_ht;   /* [2nx+2+na][2nx+2+na]  sw M + sum lamT tc                                */
 } mpx_phase_desc;
 
 typedef struct mpx_problem_desc {
@@ -153,6 +157,14 @@ int mpx_peer_close(void* dptr);
 int mpx_peer_free(void* dptr);
 int mpx_eval_g_jac_dev_peers(mpx_plan* plan, const double* d_z, const double* d_p, double* d_g, double* d_values,
                              int32_t n_peers, double* const* peer_g, double* const* peer_values, void* stream);
+
+/* -- Hessian of the Lagrangian lam_f * f + lam_g . g: replaces CasADi's nlp_hess_l(x, p, lam_f, lam_g) (derived at
+ *    mpopt.py:757; IPOPT's eval_h). LOWER triangle in CSR with sorted columns -- which is also the upper triangle in
+ *    CCS, the form CasADi returns. Built on first use. */
+int mpx_hess_structure(mpx_plan* plan, int64_t* nnz_hess, int64_t* rowptr /* n_z+1 */, int64_t* colind);
+int mpx_eval_hess_l(mpx_plan* plan, const double* z, const double* p, double lam_f, const double* lam_g, double* values);
+int mpx_eval_hess_l_dev(mpx_plan* plan, const double* d_z, const double* d_p, double lam_f, const double* d_lam_g,
+                        double* d_values, void* stream);
 
 /* -- interpolation of a solution and the dynamics residual at arbitrary points: replaces, per phase,
  *    mpopt.interpolate_single_phase + get_dynamics_residuals_single_phase (mpopt.py:1428-1542), the step after every

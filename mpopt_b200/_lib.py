@@ -23,7 +23,7 @@ c_f64p = C.POINTER(C.c_double)
 class PhaseDesc(C.Structure):
     _fields_ = [("n_path", C.c_int32), ("n_term", C.c_int32), ("pat_f", c_u8p), ("f_nz", c_u8p), ("f_t", c_u8p),
                 ("pat_c", c_u8p), ("c_t", c_u8p), ("pat_tc", c_u8p), ("diff_u", C.c_int32), ("midu", C.c_int32),
-                ("du_continuity", C.c_int32), ("cost_t", C.c_int32)]
+                ("du_continuity", C.c_int32), ("cost_t", C.c_int32), ("pat_hw", c_u8p), ("pat_ht", c_u8p)]
 
 
 class ProblemDesc(C.Structure):
@@ -78,6 +78,9 @@ PROTOTYPES = {
     "mpx_eval_jac_g": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p]),
     "mpx_eval_f_grad_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpx_eval_g_jac_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpx_hess_structure": (C.c_int, [C.c_void_p, c_i64p, c_i64p, c_i64p]),
+    "mpx_eval_hess_l": (C.c_int, [C.c_void_p, c_f64p, c_f64p, C.c_double, c_f64p, c_f64p]),
+    "mpx_eval_hess_l_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpx_eval_residuals": (C.c_int, [C.c_void_p, c_f64p, c_f64p, C.c_int32, C.c_int64, c_i32p, c_f64p, c_f64p, c_f64p,
                                      c_f64p, c_f64p, c_f64p, c_f64p]),
     "mpx_stage": (C.c_int, [C.c_void_p, c_f64p, c_f64p, C.c_int32]),

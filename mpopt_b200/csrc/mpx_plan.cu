@@ -140,7 +140,8 @@ struct PhaseLayout {
   int nc = 0, ntc = 0;
   bool has_DU = false, has_mU = false, has_dU = false;
   std::vector<int> f_next, c_len, tc_len;
-  std::vector<uint8_t> pat_f, f_nz, f_t, pat_c, c_t, pat_tc;
+  std::vector<uint8_t> pat_f, f_nz, f_t, pat_c, c_t, pat_tc, pat_hw, pat_ht;
+  bool has_hess = false;
   int64_t zoff = 0, n_g = 0;
   int64_t gF = 0, gC = 0, gDU = 0, gmU = 0, gdU = 0, gTC = 0;
   int64_t vF[MPX_MAXS], vC[MPX_MAXS];
@@ -199,6 +200,15 @@ struct mpx_plan {
   const void* rt_spec = nullptr;   // RtSpec*: run-time compiled degree-specialised kernels
   std::vector<double> h_p_cache;
   bool p_valid = false;
+  // Hessian of the Lagrangian (built on first use): lower triangle, CSR
+  bool hess_built = false;
+  std::vector<int64_t> h_rowptr, h_colind;
+  struct HessPhase {
+    DevBuf pos_yy, pos_ay, pos_ty, pos_corner, pos_term, term_assign, part;
+    int blocks = 0, n_corner = 0;
+  };
+  std::vector<HessPhase> hess_ph;
+  DevBuf d_node_seg, d_lam, d_hvals;
   std::vector<int64_t> h_tail_runs[2];  // rows of the small tail kernels (mpx_eval_g_jac_dev_peers)
   std::vector<int64_t> h_runs[3];  // shard plans: (offset, count) runs of g / values / grad_f written by this shard
   int staged = 0;                  // MPX_STAGE_* results currently valid in the device buffers (mpx_stage / mpx_fetch)
@@ -390,7 +400,7 @@ RtApi& rt_api() {
 // launches through the driver API; same interface as the AOT phases
 struct MpxRtPhase final : MpxPhaseKernels {
   CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_gjac4[2] = {nullptr, nullptr},
-               f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr}, f_resid[2] = {nullptr, nullptr};
+               f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr}, f_resid[2] = {nullptr, nullptr}, f_hess[2] = {nullptr, nullptr};
   static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st,
                         bool pdl = false) {
     RtApi& R = rt_api();
@@ -433,6 +443,10 @@ struct MpxRtPhase final : MpxPhaseKernels {
   cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const override {
     return go(f_resid[deriv], a, grid, 128, 0, st);
   }
+  cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
+    cudaError_t e = go(f_hess[0], a, grid, MPX_HESS_THREADS, 0, st);
+    return e != cudaSuccess ? e : go(f_hess[1], a, 1, 64, 0, st);
+  }
 };
 
 struct RtProgram {
@@ -474,7 +488,11 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
       for (const char* b : {"false", "true"})
         names.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ", " + b +
                         (strcmp(k, "mpx_gjac4_kernel") == 0 || strcmp(k, "mpx_gjac2_kernel") == 0 ? ", 0>" : ">"));
+  std::vector<std::string> names1;  // kernels with the phase functor as their only template argument
+  for (int ph = 0; ph < n_phases; ++ph)
+    for (const char* k : {"mpx_hess_kernel", "mpx_hess_final"}) names1.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ">");
   for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
+  for (auto& nm : names1) R.AddNameExpression(prog, nm.c_str());
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   const nvrtcResult_t rc = R.CompileProgram(prog, 3, opts);
   if (rc != 0) {
@@ -510,6 +528,14 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
           return fail(MPX_ECUDA, "kernel " + names[idx] + " not found in the run-time compiled module");
         }
       }
+    for (int b = 0; b < 2; ++b) {
+      const char* lowered = nullptr;
+      const std::string& nm = names1[(size_t)ph * 2 + b];
+      if (R.GetLoweredName(prog, nm.c_str(), &lowered) != 0 || !lowered || R.ModuleGetFunction(&P->f_hess[b], mod, lowered) != 0) {
+        R.DestroyProgram(&prog);
+        return fail(MPX_ECUDA, "kernel " + nm + " not found in the run-time compiled module");
+      }
+    }
     rp->ptrs.push_back(P.get());
     rp->phases.push_back(std::move(P));
   }
@@ -862,6 +888,9 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     copy_pat(L.pat_c, q.pat_c, (size_t)L.nc * nv);
     copy_pat(L.c_t, q.c_t, L.nc);
     copy_pat(L.pat_tc, q.pat_tc, (size_t)L.ntc * (2 * nx + 2 + na));
+    L.has_hess = q.pat_hw != nullptr && q.pat_ht != nullptr;
+    copy_pat(L.pat_hw, q.pat_hw, (size_t)(nv + 2) * (nv + 2));
+    copy_pat(L.pat_ht, q.pat_ht, (size_t)(2 * nx + 2 + na) * (2 * nx + 2 + na));
     L.has_DU = q.diff_u != 0, L.has_mU = q.midu != 0, L.has_dU = q.du_continuity != 0 && K > 1;
     L.zoff = p.nvar * ph;
     L.cost_t = q.cost_t != 0;
@@ -1419,6 +1448,214 @@ extern "C" int mpx_eval_grad_f(mpx_plan* p, const double* z, const double* pw, d
   if (rc) return rc;
   if (f) CUDA_TRY(cudaMemcpyAsync(f, p->d_f.p, sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaMemcpyAsync(grad, p->d_grad.p, (size_t)p->n_z * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+// ------------------------------------------------------------------ Hessian of the Lagrangian
+namespace {
+// entry order and categories of the node Hessian: identical to mpopt_b200/program.py::PhaseProgram.hess_layout
+struct HessEntry { int a, b, cat, slot; };
+
+int build_hessian(mpx_plan& p) {
+  if (p.hess_built) return MPX_OK;
+  if (p.seg_begin != 0 || p.seg_end != p.K) return fail(MPX_EINVAL, "the Hessian needs a plan over all segments");
+  for (auto& L : p.ph)
+    if (!L.has_hess) return fail(MPX_ENOPROGRAM, "the problem description carries no Hessian patterns (pat_hw / pat_ht)");
+  const int nx = p.nx, nu = p.nu, na = p.na, ny = nx + nu, nv = ny + na, N = p.N, NW = nv + 2, NT = 2 * nx + 2 + na;
+  const int it = nv, ih = nv + 1;
+  std::vector<std::pair<int64_t, int64_t>> trip;
+  std::vector<std::vector<HessEntry>> ents(p.P);
+  std::vector<std::vector<int>> tys(p.P);
+  auto colv = [&](const PhaseLayout& L, int q, int64_t i) { return L.zoff + (int64_t)q * N + i; };  // node variable q < ny
+  auto colT0 = [&](const PhaseLayout& L) { return L.zoff + (int64_t)ny * N; };
+  auto colA = [&](const PhaseLayout& L, int m) { return L.zoff + (int64_t)ny * N + 2 + m; };
+  auto termcol = [&](const PhaseLayout& L, int v) -> int64_t {  // xf.., x0.., tf, t0, a..
+    if (v < nx) return colv(L, v, N - 1);
+    if (v < 2 * nx) return colv(L, v - nx, 0);
+    if (v == 2 * nx) return colT0(L) + 1;
+    if (v == 2 * nx + 1) return colT0(L);
+    return colA(L, v - 2 * nx - 2);
+  };
+  auto corner_cols = [&](const PhaseLayout& L, int c, int64_t& r, int64_t& cc) {
+    if (c == 0) r = colT0(L), cc = colT0(L);
+    else if (c == 1) r = colT0(L) + 1, cc = colT0(L);
+    else if (c == 2) r = colT0(L) + 1, cc = colT0(L) + 1;
+    else if (c < 3 + 2 * na) r = colA(L, (c - 3) / 2), cc = colT0(L) + ((c - 3) & 1);
+    else {
+      int m = 0, rem = c - 3 - 2 * na;
+      while (rem > m) rem -= m + 1, ++m;
+      r = colA(L, m), cc = colA(L, rem);
+    }
+  };
+  const int n_corner = 3 + 2 * na + na * (na + 1) / 2;
+  std::vector<std::vector<uint8_t>> corner_on(p.P, std::vector<uint8_t>(n_corner, 0));
+  for (int ph = 0; ph < p.P; ++ph) {
+    const PhaseLayout& L = p.ph[ph];
+    std::vector<int>& ty = tys[ph];
+    for (int b = 0; b < ny; ++b)
+      if (L.pat_hw[(size_t)it * NW + b] || L.pat_hw[(size_t)ih * NW + b]) ty.push_back(b);
+    int n_yy = 0, n_ay = 0;
+    for (int a = 0; a < NW; ++a)
+      for (int b = 0; b <= a; ++b) {
+        if (!L.pat_hw[(size_t)a * NW + b]) continue;
+        HessEntry e{a, b, 0, 0};
+        if (a < ny) e.cat = 0, e.slot = n_yy++;
+        else if (a < nv && b < ny) e.cat = 1, e.slot = n_ay++;
+        else if (a < nv) e.cat = 2, e.slot = 3 + 2 * na + (a - ny) * (a - ny + 1) / 2 + (b - ny);
+        else if (b < ny) e.cat = a == it ? 3 : 4, e.slot = (int)(std::find(ty.begin(), ty.end(), b) - ty.begin());
+        else if (b < nv) e.cat = a == it ? 5 : 6, e.slot = b - ny;
+        else if (a == it) e.cat = 7;
+        else e.cat = 8;
+        ents[ph].push_back(e);
+        // structural entries
+        if (e.cat == 0)
+          for (int64_t i = 0; i < N; ++i) trip.emplace_back(colv(L, a, i), colv(L, b, i));
+        else if (e.cat == 1)
+          for (int64_t i = 0; i < N; ++i) trip.emplace_back(colA(L, a - ny), colv(L, b, i));
+        else if (e.cat == 2) corner_on[ph][e.slot] = 1;
+        else if (e.cat == 5 || e.cat == 6) corner_on[ph][3 + 2 * e.slot] = corner_on[ph][3 + 2 * e.slot + 1] = 1;
+        else if (e.cat == 7 || e.cat == 8) corner_on[ph][0] = corner_on[ph][1] = corner_on[ph][2] = 1;
+      }
+    for (int b : ty)
+      for (int64_t i = 0; i < N; ++i) trip.emplace_back(colT0(L), colv(L, b, i)), trip.emplace_back(colT0(L) + 1, colv(L, b, i));
+    for (int c = 0; c < n_corner; ++c)
+      if (corner_on[ph][c]) {
+        int64_t r, cc;
+        corner_cols(L, c, r, cc);
+        trip.emplace_back(r, cc);
+      }
+    for (int a = 0; a < NT; ++a)
+      for (int b = 0; b <= a; ++b)
+        if (L.pat_ht[(size_t)a * NT + b]) {
+          const int64_t ca = termcol(L, a), cb = termcol(L, b);
+          trip.emplace_back(std::max(ca, cb), std::min(ca, cb));
+        }
+  }
+  std::sort(trip.begin(), trip.end());
+  trip.erase(std::unique(trip.begin(), trip.end()), trip.end());
+  p.h_rowptr.assign((size_t)p.n_z + 1, 0);
+  p.h_colind.resize(trip.size());
+  for (size_t e = 0; e < trip.size(); ++e) ++p.h_rowptr[(size_t)trip[e].first + 1], p.h_colind[e] = trip[e].second;
+  for (int64_t r = 0; r < p.n_z; ++r) p.h_rowptr[(size_t)r + 1] += p.h_rowptr[(size_t)r];
+  auto pos_of = [&](int64_t r, int64_t c) -> int64_t {
+    const int64_t* b = p.h_colind.data() + p.h_rowptr[(size_t)r];
+    const int64_t* e = p.h_colind.data() + p.h_rowptr[(size_t)r + 1];
+    return std::lower_bound(b, e, c) - p.h_colind.data();
+  };
+  // which terminal entries share their position with a node / corner entry?  mark the node-owned positions
+  std::vector<uint8_t> owned(trip.size(), 0);
+  p.hess_ph.resize(p.P);
+  auto upload = [&](DevBuf& b, const void* src, size_t bytes) -> cudaError_t {
+    cudaError_t e = b.ensure(bytes ? bytes : 8);
+    if (e != cudaSuccess || !bytes) return e;
+    return cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+  };
+  CUDA_TRY(cudaSetDevice(p.device));
+  for (int ph = 0; ph < p.P; ++ph) {
+    const PhaseLayout& L = p.ph[ph];
+    auto& H = p.hess_ph[ph];
+    std::vector<int64_t> pyy, pay, pty, pcorner(n_corner, -1);
+    const size_t nty = tys[ph].size();
+    pty.resize(2 * nty * (size_t)N);
+    for (const HessEntry& e : ents[ph]) {
+      if (e.cat == 0) {
+        pyy.resize(pyy.size() + N);
+        for (int64_t i = 0; i < N; ++i) owned[pyy[(size_t)e.slot * N + i] = pos_of(colv(L, e.a, i), colv(L, e.b, i))] = 1;
+      } else if (e.cat == 1) {
+        pay.resize(pay.size() + N);
+        for (int64_t i = 0; i < N; ++i) owned[pay[(size_t)e.slot * N + i] = pos_of(colA(L, e.a - ny), colv(L, e.b, i))] = 1;
+      }
+    }
+    for (size_t q = 0; q < nty; ++q)
+      for (int64_t i = 0; i < N; ++i) {
+        owned[pty[q * N + i] = pos_of(colT0(L), colv(L, tys[ph][q], i))] = 1;
+        owned[pty[(nty + q) * N + i] = pos_of(colT0(L) + 1, colv(L, tys[ph][q], i))] = 1;
+      }
+    for (int c = 0; c < n_corner; ++c)
+      if (corner_on[ph][c]) {
+        int64_t r, cc;
+        corner_cols(L, c, r, cc);
+        owned[pcorner[c] = pos_of(r, cc)] = 1;
+      }
+    std::vector<int64_t> pterm;
+    std::vector<int32_t> tassign;
+    for (int a = 0; a < NT; ++a)
+      for (int b = 0; b <= a; ++b)
+        if (L.pat_ht[(size_t)a * NT + b]) {
+          const int64_t ca = termcol(L, a), cb = termcol(L, b);
+          const int64_t pos = pos_of(std::max(ca, cb), std::min(ca, cb));
+          pterm.push_back(pos), tassign.push_back(owned[pos] ? 0 : 1);
+        }
+    CUDA_TRY(upload(H.pos_yy, pyy.data(), pyy.size() * sizeof(int64_t)));
+    CUDA_TRY(upload(H.pos_ay, pay.data(), pay.size() * sizeof(int64_t)));
+    CUDA_TRY(upload(H.pos_ty, pty.data(), pty.size() * sizeof(int64_t)));
+    CUDA_TRY(upload(H.pos_corner, pcorner.data(), pcorner.size() * sizeof(int64_t)));
+    CUDA_TRY(upload(H.pos_term, pterm.data(), pterm.size() * sizeof(int64_t)));
+    CUDA_TRY(upload(H.term_assign, tassign.data(), tassign.size() * sizeof(int32_t)));
+    H.blocks = (N + MPX_HESS_THREADS - 1) / MPX_HESS_THREADS, H.n_corner = n_corner;
+    CUDA_TRY(H.part.ensure((size_t)H.blocks * n_corner * sizeof(double)));
+  }
+  std::vector<int32_t> node_seg((size_t)N, 0);
+  for (int k = 0; k < p.K; ++k)
+    for (int j = (k == 0 ? 0 : 1); j <= p.po[k]; ++j) node_seg[(size_t)p.seg_start[k] + j] = k;  // shared node: earlier segment
+  CUDA_TRY(upload(p.d_node_seg, node_seg.data(), node_seg.size() * sizeof(int32_t)));
+  CUDA_TRY(p.d_lam.ensure((size_t)p.n_g * sizeof(double)));
+  CUDA_TRY(p.d_hvals.ensure(p.h_colind.size() * sizeof(double)));
+  p.hess_built = true;
+  return MPX_OK;
+}
+
+int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f, const double* d_lam, double* d_vals,
+                cudaStream_t st) {
+  mpx_scan_widths_kernel<<<p.P, 32, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
+  ++p.launches;
+  for (int ph = 0; ph < p.P; ++ph) {
+    MpxPhaseArgs a = p.args[ph];
+    auto& H = p.hess_ph[ph];
+    a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
+    a.lam = d_lam, a.lam_f = lam_f, a.node_seg = p.d_node_seg.as<int32_t>();
+    a.hp_yy = H.pos_yy.as<int64_t>(), a.hp_ay = H.pos_ay.as<int64_t>(), a.hp_ty = H.pos_ty.as<int64_t>();
+    a.hp_corner = H.pos_corner.as<int64_t>(), a.hp_term = H.pos_term.as<int64_t>();
+    a.hp_term_assign = H.term_assign.as<int32_t>();
+    a.hvals = d_vals, a.hpart = H.part.as<double>(), a.h_blocks = H.blocks;
+    CUDA_TRY(p.prog->phases[ph]->hess(a, H.blocks, st));
+    p.launches += 2;
+  }
+  return MPX_OK;
+}
+}  // namespace
+
+extern "C" int mpx_hess_structure(mpx_plan* p, int64_t* nnz, int64_t* rowptr, int64_t* colind) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  int rc = build_hessian(*p);
+  if (rc) return rc;
+  if (nnz) *nnz = (int64_t)p->h_colind.size();
+  if (rowptr) memcpy(rowptr, p->h_rowptr.data(), p->h_rowptr.size() * sizeof(int64_t));
+  if (colind) memcpy(colind, p->h_colind.data(), p->h_colind.size() * sizeof(int64_t));
+  return MPX_OK;
+}
+
+extern "C" int mpx_eval_hess_l_dev(mpx_plan* p, const double* d_z, const double* d_p, double lam_f, const double* d_lam_g,
+                                   double* d_values, void* stream) {
+  if (!p || !d_z || !d_p || !d_lam_g || !d_values) return fail(MPX_EINVAL, "NULL argument");
+  int rc = build_hessian(*p);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(p->device));
+  return launch_hess(*p, d_z, d_p, lam_f, d_lam_g, d_values, stream ? static_cast<cudaStream_t>(stream) : p->stream);
+}
+
+extern "C" int mpx_eval_hess_l(mpx_plan* p, const double* z, const double* pw, double lam_f, const double* lam_g,
+                               double* values) {
+  if (!p || !lam_g || !values) return fail(MPX_EINVAL, "NULL argument");
+  int rc = build_hessian(*p);
+  if (rc) return rc;
+  rc = upload_inputs(*p, z, pw);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(p->d_lam.p, lam_g, (size_t)p->n_g * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  rc = launch_hess(*p, p->d_z.as<double>(), p->d_p.as<double>(), lam_f, p->d_lam.as<double>(), p->d_hvals.as<double>(), p->stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(values, p->d_hvals.p, p->h_colind.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;
 }

@@ -22,6 +22,7 @@ struct MpxPhaseKernels {
   virtual cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const = 0;
   virtual cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const = 0;
+  virtual cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const = 0;  // node kernel + final
 };
 
 struct MpxProgramEntry {
@@ -141,6 +142,11 @@ struct MpxAotPhase final : MpxPhaseKernels {
   cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const override {
     if (deriv) mpx_residual_kernel<PH, true><<<grid, 128, 0, st>>>(a);
     else mpx_residual_kernel<PH, false><<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
+    mpx_hess_kernel<PH><<<grid, MPX_HESS_THREADS, 0, st>>>(a);
+    mpx_hess_final<PH><<<1, 64, 0, st>>>(a);
     return cudaGetLastError();
   }
 };

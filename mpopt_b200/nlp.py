@@ -49,11 +49,12 @@ class Transcription:
             mid = bool(o.midu[ph]) and bool((np.asarray(o.lbu[ph]) > -np.inf).any() or
                                             (np.asarray(o.ubu[ph]) < np.inf).any())  # mpopt.py:346, :363-365
             self.has_mU.append(mid)
-            arrs = [_u8(pp.pat_f()), _u8(pp.f_nz), _u8(pp.f_t()), _u8(pp.pat_c()), _u8(pp.c_t()), _u8(pp.pat_tc())]
+            arrs = [_u8(pp.pat_f()), _u8(pp.f_nz), _u8(pp.f_t()), _u8(pp.pat_c()), _u8(pp.c_t()), _u8(pp.pat_tc()),
+                    _u8(pp.pat_hw()), _u8(pp.pat_ht())]
             self._keep += arrs
             d = phases[ph]
             d.n_path, d.n_term = pp.nc, pp.ntc
-            d.pat_f, d.f_nz, d.f_t, d.pat_c, d.c_t, d.pat_tc = [_lib.ptr(a, _lib.c_u8p) for a in arrs]
+            d.pat_f, d.f_nz, d.f_t, d.pat_c, d.c_t, d.pat_tc, d.pat_hw, d.pat_ht = [_lib.ptr(a, _lib.c_u8p) for a in arrs]
             d.diff_u, d.midu = int(bool(o.diff_u[ph])), int(mid)
             d.du_continuity = int(bool(o.du_continuity[ph]))
             d.cost_t = int(not pp.Lt.is_value(0.0))
@@ -156,6 +157,34 @@ class Transcription:
 
         rp, ci = self.structure()
         return sp.csr_matrix((self.jac_g_values(z, p), ci, rp), shape=(self.n_g, self.n_z))
+
+    # ------------------------------------------------------------------ Hessian of the Lagrangian
+    def hess_structure(self):
+        """(rowptr, colind) of the lower triangle of the Lagrangian Hessian, CSR, int64, sorted columns."""
+        if getattr(self, "_hstructure", None) is None:
+            n = C.c_int64()
+            _lib.check(self._L.mpx_hess_structure(self._plan, C.byref(n), None, None))
+            rp, ci = np.empty(self.n_z + 1, np.int64), np.empty(n.value, np.int64)
+            _lib.check(self._L.mpx_hess_structure(self._plan, None, _lib.ptr(rp, _lib.c_i64p), _lib.ptr(ci, _lib.c_i64p)))
+            self._hstructure = (rp, ci)
+        return self._hstructure
+
+    def hess_l_values(self, z, p=None, lam_f=1.0, lam_g=None, out=None):
+        z, p = self._zp(z, p)
+        lam = np.zeros(self.n_g) if lam_g is None else np.ascontiguousarray(lam_g, dtype=float)
+        if lam.shape != (self.n_g,):
+            raise ValueError(f"expected lam_g of shape ({self.n_g},)")
+        nnz = len(self.hess_structure()[1])
+        out = np.empty(nnz) if out is None else out
+        _lib.check(self._L.mpx_eval_hess_l(self._plan, _lib.ptr(z), _lib.ptr(p), float(lam_f), _lib.ptr(lam), _lib.ptr(out)))
+        return out
+
+    def hess_l(self, z, p=None, lam_f=1.0, lam_g=None):
+        """Lower triangle of the Hessian of ``lam_f * f + lam_g . g`` as scipy.sparse.csr_matrix (CasADi's nlp_hess_l)."""
+        import scipy.sparse as sp
+
+        rp, ci = self.hess_structure()
+        return sp.csr_matrix((self.hess_l_values(z, p, lam_f, lam_g), ci, rp), shape=(self.n_z, self.n_z))
 
     # ------------------------------------------------------------------ interpolation / residuals (SURVEY 8f N3)
     def residuals(self, z, p=None, phase=0, taus=None, derivatives=True):

@@ -76,6 +76,84 @@ class PhaseProgram:
             self.jtc += [(r, v, d) for v, d in enumerate(g) if not d.is_value(0.0)]
         self.gM = [(v, d) for v, d in enumerate(tr.gradient(self.M, self.term_vars)) if not d.is_value(0.0)]
 
+        # ---- Hessian of the Lagrangian (CasADi's nlp_hess_l, implicit in mpopt.py:757).  At one node
+        #      lag = h (sw L - sum_s lamF_s Sx_s f_s) + sum_q lamC_q c_q  with the segment width h and the multipliers as
+        #      extra symbols; second derivatives w.r.t. W = (x.., u.., a.., t, h), lower triangle.  The kernel maps
+        #      (t, h) -> (T0, TF) with the (linear) chain rule.
+        self.hs, self.sw = tr.var(f"{tag}hs"), tr.var(f"{tag}sw")
+        self.lamF = [tr.var(f"{tag}lf{s}") for s in range(nx)]
+        self.lamC = [tr.var(f"{tag}lc{q}") for q in range(self.nc)]
+        self.sxs = [tr.var(f"{tag}sx{s}") for s in range(nx)]
+        phi = tr.mul(self.sw, self.L)
+        for s in range(nx):
+            phi = tr.sub(phi, tr.mul(tr.mul(self.lamF[s], self.sxs[s]), self.f[s]))
+        lag = tr.mul(self.hs, phi)
+        for q in range(self.nc):
+            lag = tr.add(lag, tr.mul(self.lamC[q], self.c[q]))
+        self.hess_vars = self.node_vars + [self.t, self.hs]
+        self.hw = self._lower_hessian(lag, self.hess_vars)  # [(a, b, Expr)], b <= a
+        self.lamT = [tr.var(f"{tag}lt{r}") for r in range(self.ntc)]
+        theta = tr.mul(self.sw, self.M)
+        for r in range(self.ntc):
+            theta = tr.add(theta, tr.mul(self.lamT[r], self.tc[r]))
+        self.ht = self._lower_hessian(theta, self.term_vars)
+
+    @staticmethod
+    def _lower_hessian(scalar, wrt):
+        g = tr.gradient(scalar, wrt)
+        ent = []
+        for a, ga in enumerate(g):
+            if ga.is_value(0.0):
+                continue
+            for b, d in enumerate(tr.gradient(ga, wrt[: a + 1])):
+                if not d.is_value(0.0):
+                    ent.append((a, b, d))
+        return ent
+
+    def pat_hw(self):
+        n = len(self.hess_vars)
+        p = [[0] * n for _ in range(n)]
+        for a, b, _ in self.hw:
+            p[a][b] = 1
+        return p
+
+    def pat_ht(self):
+        n = len(self.term_vars)
+        p = [[0] * n for _ in range(n)]
+        for a, b, _ in self.ht:
+            p[a][b] = 1
+        return p
+
+    def hess_layout(self):
+        """Categories and slots of the node Hessian entries, shared by the code generator and Layout:
+        cat 0 YY (slot = ordinal), 1 AY (ordinal), 2 AA (corner index), 3 tY, 4 hY (slot = ordinal of q among the node
+        variables coupled to T0 / TF), 5 tA, 6 hA (slot = m), 7 tt, 8 ht."""
+        ny, na, nv = self.nx + self.nu, self.na, self.nv
+        it, ih = nv, nv + 1
+        ty = sorted({b for a, b, _ in self.hw if a in (it, ih) and b < ny})
+        cat, slot = [], []
+        n_yy = n_ay = 0
+        for a, b, _ in self.hw:
+            if a < ny:
+                cat.append(0), slot.append(n_yy)
+                n_yy += 1
+            elif a < nv and b < ny:
+                cat.append(1), slot.append(n_ay)
+                n_ay += 1
+            elif a < nv:
+                m, n = a - ny, b - ny
+                cat.append(2), slot.append(3 + 2 * na + m * (m + 1) // 2 + n)
+            elif b < ny:
+                cat.append(3 if a == it else 4), slot.append(ty.index(b))
+            elif b < nv:
+                cat.append(5 if a == it else 6), slot.append(b - ny)
+            elif a == it:
+                cat.append(7), slot.append(0)
+            else:
+                assert b == it, "d2/dh2 is structurally zero"
+                cat.append(8), slot.append(0)
+        return dict(cat=cat, slot=slot, ty=ty, n_yy=n_yy, n_ay=n_ay, n_corner=3 + 2 * na + na * (na + 1) // 2)
+
     # ---- structural patterns handed to the C ABI (uint8 row-major)
     @property
     def nv(self):
@@ -232,6 +310,17 @@ class PhaseProgram:
         L.append(self._switch("jtc_pos", jtc_pos))
         L.append(self._switch("jtc_var", jtc_var))
         L.append(self._switch("gm_var", [v for v, _ in self.gM]))
+        # -- Lagrangian Hessian
+        hl = self.hess_layout()
+        L.append(f"  static constexpr int NHW = {len(self.hw)}, NHT = {len(self.ht)}, NH_YY = {hl['n_yy']}, "
+                 f"NH_AY = {hl['n_ay']}, NH_TY = {len(hl['ty'])}, NH_CORNER = {hl['n_corner']};")
+        L.append(self._switch("hw_a", [a for a, _, _ in self.hw]))
+        L.append(self._switch("hw_b", [b for _, b, _ in self.hw]))
+        L.append(self._switch("hw_cat", hl["cat"]))
+        L.append(self._switch("hw_slot", hl["slot"]))
+        L.append(self._switch("h_ty_var", hl["ty"]))
+        L.append(self._switch("ht_a", [a for a, _, _ in self.ht]))
+        L.append(self._switch("ht_b", [b for _, b, _ in self.ht]))
 
         def fn(sig, outs, targets, ref, prefix):
             lines, refs = tr.emit_c(outs, ref, indent="    ", prefix=prefix)
@@ -273,6 +362,19 @@ class PhaseProgram:
               + [f"gm[{e}]" for e in range(len(self.gM))])
         L += fn(f"term({term_sig}, double* __restrict__ tc, double* __restrict__ jtc, double* __restrict__ M, "
                 f"double* __restrict__ gm)", outs, tg, self._term_ref(), "m")
+        ref = self._var_ref()
+        ref[self.hs.name], ref[self.sw.name] = "h", "sw"
+        ref.update({v.name: f"lf[{i}]" for i, v in enumerate(self.lamF)})
+        ref.update({v.name: f"lc[{i}]" for i, v in enumerate(self.lamC)})
+        ref.update({v.name: f"sxs[{i}]" for i, v in enumerate(self.sxs)})
+        L += fn(f"hess_node({node_sig}, const double h, const double sw, const double* __restrict__ lf, "
+                f"const double* __restrict__ lc, const double* __restrict__ sxs, double* __restrict__ hw)",
+                [d for _, _, d in self.hw], [f"hw[{e}]" for e in range(len(self.hw))], ref, "w")
+        ref = self._term_ref()
+        ref[self.sw.name] = "sw"
+        ref.update({v.name: f"lt[{i}]" for i, v in enumerate(self.lamT)})
+        L += fn(f"hess_term({term_sig}, const double sw, const double* __restrict__ lt, double* __restrict__ ht)",
+                [d for _, _, d in self.ht], [f"ht[{e}]" for e in range(len(self.ht))], ref, "z")
         L.append("};")
         return "\n".join(L)
 

@@ -373,3 +373,29 @@ def test_interpolation_and_residuals_match_oracle(libmpx, problem, K, po, scheme
             assert_close(got["dxi"], DXi, "DXi")
             assert_close(got["dui"], DUi, "DUi")
             assert_close(got["res"], res, "residual")
+
+
+@pytest.mark.parametrize("problem,K,po,scheme", [("moon_lander", 6, 4, "LGR"), ("kitchen_sink", 5, [3, 2, 4, 5, 3], "LGL"),
+                                                 ("two_phase_schwartz", 4, 6, "LGR"), ("van_der_pol", 3, [2, 5, 3], "CGL"),
+                                                 ("robot_arm", 7, 5, "LGR"), ("synthetic_6_3", 33, 15, "LGR"),
+                                                 ("hyper_sensitive", 3, 9, "LGL"), ("generic_two_phase", 3, [2, 5, 3], "CGL")])
+def test_lagrangian_hessian_matches_oracle(libmpx, problem, K, po, scheme):
+    """nlp_hess_l(x, p, lam_f, lam_g) -- lower triangle, CSR -- against the oracle's second-order
+    dual-number restatement: pattern bit-exact, values to 1e-10."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle.hessian import hess_l
+    from oracle.nlp import OracleNLP
+
+    tr = Transcription(REGISTRY[problem](), K, po, scheme)
+    ora = OracleNLP(REGISTRY[problem](), K, po, scheme)
+    z, p = random_point(ora, dirichlet=True)
+    rng = np.random.default_rng(4)
+    lam, sig = rng.uniform(-1, 1, ora.n_g), 0.6
+    H = hess_l(ora, z, p, sig, lam)
+    rp, ci = tr.hess_structure()
+    assert np.array_equal(rp, H.indptr) and np.array_equal(ci, H.indices), "Hessian pattern differs from the oracle"
+    assert_close(tr.hess_l_values(z, p, sig, lam), H.data, "hess_l values")
+    # a second point and other multipliers through the same plan (positions are reused, nothing stale is left behind)
+    z2, lam2 = z + 1e-2, rng.uniform(-2, 2, ora.n_g)
+    assert_close(tr.hess_l_values(z2, p, 1.0, lam2), hess_l(ora, z2, p, 1.0, lam2).data, "hess_l values, second point")
