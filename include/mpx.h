@@ -191,8 +191,8 @@ int mpx_fetch(mpx_plan* plan, int32_t what, double* out);   /* F: 1, GRAD: n_z, 
 
 /* -- IPOPT C interface (IpStdCInterface.h: Eval_F_CB, Eval_Grad_F_CB, Eval_G_CB, Eval_Jac_G_CB): pass these four
  *    functions to CreateIpoptProblem and a filled mpx_ipopt_data as user_data. Index = int, Number = double,
- *    Bool = int (only the low byte of new_x is read, so a C99 bool works too); index_style 0 (C). eval_jac_g with
- *    values == NULL writes the CSR pattern as triplets. No Eval_H_CB: use hessian_approximation limited-memory. */
+ *    Bool = int (only the low byte of new_x is read, so a C99 bool works too); index_style 0 (C). eval_jac_g / eval_h
+ *    with values == NULL write the pattern as triplets. */
 typedef struct mpx_ipopt_data {
   mpx_plan* plan;
   const double* p;  /* segment-width fractions (the NLP parameter vector, mpopt.py:631) */
@@ -202,6 +202,9 @@ int mpx_ipopt_eval_grad_f(int n, const double* x, int new_x, double* grad_f, voi
 int mpx_ipopt_eval_g(int n, const double* x, int new_x, int m, double* g, void* user_data);
 int mpx_ipopt_eval_jac_g(int n, const double* x, int new_x, int m, int nele_jac, int* iRow, int* jCol, double* values,
                          void* user_data);
+/* Eval_H_CB: lower triangle of obj_factor * hess f + sum lambda_i hess g_i (nele_hess from mpx_hess_structure) */
+int mpx_ipopt_eval_h(int n, const double* x, int new_x, double obj_factor, int m, const double* lambda, int new_lambda,
+                     int nele_hess, int* iRow, int* jCol, double* values, void* user_data);
 
 /* -- CasADi external functions (the ABI of CasADi's generated C code, as loaded by ca.external(name, lib) and by
  *    ca.nlpsol(name, plugin, lib)): nlp_f (x,p)->(f), nlp_g (x,p)->(g), nlp_grad_f (x,p)->(f, grad_f_x),
@@ -231,6 +234,7 @@ MPX_CASADI_DECLARE(nlp_f)
 MPX_CASADI_DECLARE(nlp_g)
 MPX_CASADI_DECLARE(nlp_grad_f)
 MPX_CASADI_DECLARE(nlp_jac_g)
+MPX_CASADI_DECLARE(nlp_hess_l) /* (x, p, lam_f, lam_g) -> (hess_gamma_x_x): upper triangle, CCS */
 
 /* number of kernel launches issued by this plan so far (bench.py's gpu_launches) */
 int64_t mpx_launch_count(const mpx_plan* plan);

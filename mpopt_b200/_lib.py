@@ -44,7 +44,7 @@ class IpoptData(C.Structure):
 MPX_STAGE_F, MPX_STAGE_GRAD, MPX_STAGE_G, MPX_STAGE_JAC, MPX_FETCH_JAC_CCS = 1, 2, 4, 8, 16
 
 #: CasADi external-function symbols exported for each of these names (include/mpx.h, MPX_CASADI_DECLARE)
-CASADI_FUNCTIONS = ("nlp_f", "nlp_g", "nlp_grad_f", "nlp_jac_g")
+CASADI_FUNCTIONS = ("nlp_f", "nlp_g", "nlp_grad_f", "nlp_jac_g", "nlp_hess_l")
 CASADI_SUFFIXES = ("", "_n_in", "_n_out", "_default_in", "_name_in", "_name_out", "_sparsity_in", "_sparsity_out",
                    "_work", "_alloc_mem", "_init_mem", "_free_mem", "_checkout", "_release", "_incref", "_decref")
 
@@ -91,6 +91,8 @@ PROTOTYPES = {
     "mpx_ipopt_eval_g": (C.c_int, [C.c_int, c_f64p, C.c_int, C.c_int, c_f64p, C.c_void_p]),
     "mpx_ipopt_eval_jac_g": (C.c_int, [C.c_int, c_f64p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int),
                                        C.POINTER(C.c_int), c_f64p, C.c_void_p]),
+    "mpx_ipopt_eval_h": (C.c_int, [C.c_int, c_f64p, C.c_int, C.c_double, C.c_int, c_f64p, C.c_int, C.c_int,
+                                   C.POINTER(C.c_int), C.POINTER(C.c_int), c_f64p, C.c_void_p]),
     "mpx_casadi_bind": (C.c_int, [C.c_void_p]),
     "mpx_sync": (C.c_int, [C.c_void_p]),
     "mpx_peer_alloc": (C.c_int, [C.c_int32, C.c_int64, C.POINTER(C.c_void_p), C.c_void_p]),

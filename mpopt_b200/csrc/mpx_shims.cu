@@ -5,6 +5,7 @@
 //   * CasADi's external-function ABI for nlp_f / nlp_g / nlp_grad_f / nlp_jac_g, the functions ca.nlpsol derives at
 //     mpopt.py:757 (names as printed in the reference's stored timing tables, e.g.
 //     docs/source/notebooks/moon_lander.ipynb:204-209).
+//   * nlp_hess_l (x, p, lam_f, lam_g) -> triu Hessian of the Lagrangian, and IPOPT's Eval_H_CB.
 // Neither IPOPT nor CasADi is present in this image, so these are exercised through their C calling conventions
 // by tests/test_shims.py, not by the real solvers.
 #include <string.h>
@@ -66,13 +67,33 @@ extern "C" int mpx_ipopt_eval_jac_g(int n, const double* x, int new_x, int m, in
   return mpx_fetch(d->plan, MPX_STAGE_JAC, values) == MPX_OK;
 }
 
+// Eval_H_CB: lower triangle of sigma * hess f + sum lambda_i hess g_i.  values == NULL: the pattern as triplets.
+extern "C" int mpx_ipopt_eval_h(int n, const double* x, int new_x, double obj_factor, int m, const double* lambda,
+                                int new_lambda, int nele_hess, int* iRow, int* jCol, double* values, void* user_data) {
+  (void)new_x, (void)new_lambda;  // the Hessian kernel is cheap next to the Jacobian: always evaluated from (x, lambda)
+  mpx_ipopt_data* d = static_cast<mpx_ipopt_data*>(user_data);
+  if (!d || !d->plan || !d->p || !sizes_ok(d->plan, n, m, -1)) return 0;
+  int64_t nnz = 0;
+  if (mpx_hess_structure(d->plan, &nnz, nullptr, nullptr) != MPX_OK || nnz != nele_hess) return 0;
+  if (!values) {
+    if (!iRow || !jCol) return 0;
+    std::vector<int64_t> rp((size_t)n + 1), ci((size_t)nnz);
+    if (mpx_hess_structure(d->plan, nullptr, rp.data(), ci.data()) != MPX_OK) return 0;
+    for (int r = 0; r < n; ++r)
+      for (int64_t e = rp[r]; e < rp[r + 1]; ++e) iRow[e] = r, jCol[e] = (int)ci[e];
+    return 1;
+  }
+  if (!x || !lambda) return 0;
+  return mpx_eval_hess_l(d->plan, x, d->p, obj_factor, lambda, values) == MPX_OK;
+}
+
 // ------------------------------------------------------------------ CasADi external functions
 namespace {
 struct Bound {
   mpx_plan* plan = nullptr;
   int64_t n_z = 0, n_p = 0, n_g = 0, nnz = 0;
   // compact CCS patterns [nrow, ncol, colind[ncol+1], row[nnz]] (CasADi's casadi_int = long long)
-  std::vector<long long> sp_x, sp_p, sp_f, sp_g, sp_jac;
+  std::vector<long long> sp_x, sp_p, sp_f, sp_g, sp_jac, sp_hess;
 } B;
 
 std::vector<long long> dense_col(int64_t n) {
@@ -99,6 +120,16 @@ extern "C" int mpx_casadi_bind(mpx_plan* plan) {
   b.sp_jac.push_back(b.n_g), b.sp_jac.push_back(b.n_z);
   for (int64_t v : cp) b.sp_jac.push_back(v);
   for (int64_t v : ri) b.sp_jac.push_back(v);
+  // Hessian: the lower triangle in CSR is the upper triangle in CCS (CasADi's hess_gamma_x_x); optional
+  int64_t hn = 0;
+  if (mpx_hess_structure(plan, &hn, nullptr, nullptr) == MPX_OK) {
+    std::vector<int64_t> rp((size_t)b.n_z + 1), ci((size_t)hn);
+    if (mpx_hess_structure(plan, nullptr, rp.data(), ci.data()) == MPX_OK) {
+      b.sp_hess.push_back(b.n_z), b.sp_hess.push_back(b.n_z);
+      for (int64_t v : rp) b.sp_hess.push_back(v);
+      for (int64_t v : ci) b.sp_hess.push_back(v);
+    }
+  }
   B = std::move(b);
   return MPX_OK;
 }
@@ -166,3 +197,39 @@ MPX_CASADI_DEFINE(nlp_f, 0, 1)
 MPX_CASADI_DEFINE(nlp_g, 1, 1)
 MPX_CASADI_DEFINE(nlp_grad_f, 2, 2)
 MPX_CASADI_DEFINE(nlp_jac_g, 3, 2)
+
+// nlp_hess_l (x, p, lam_f, lam_g) -> (hess_gamma_x_x): triu of the Lagrangian Hessian in CCS
+extern "C" int nlp_hess_l(const double** arg, double** res, long long*, double*, int) {
+  if (!B.plan || B.sp_hess.empty() || !arg || !res || !arg[0] || !arg[1] || !arg[2] || !arg[3]) return 1;
+  if (!res[0]) return 0;
+  return mpx_eval_hess_l(B.plan, arg[0], arg[1], arg[2][0], arg[3], res[0]) == MPX_OK ? 0 : 1;
+}
+extern "C" long long nlp_hess_l_n_in(void) { return 4; }
+extern "C" long long nlp_hess_l_n_out(void) { return 1; }
+extern "C" double nlp_hess_l_default_in(long long) { return 0.0; }
+extern "C" const char* nlp_hess_l_name_in(long long i) {
+  static const char* n[4] = {"x", "p", "lam_f", "lam_g"};
+  return i >= 0 && i < 4 ? n[i] : nullptr;
+}
+extern "C" const char* nlp_hess_l_name_out(long long i) { return i == 0 ? "hess_gamma_x_x" : nullptr; }
+extern "C" const long long* nlp_hess_l_sparsity_in(long long i) {
+  if (!B.plan) return nullptr;
+  return i == 0 ? B.sp_x.data() : i == 1 ? B.sp_p.data() : i == 2 ? B.sp_f.data() : i == 3 ? B.sp_g.data() : nullptr;
+}
+extern "C" const long long* nlp_hess_l_sparsity_out(long long i) {
+  return (B.plan && i == 0 && !B.sp_hess.empty()) ? B.sp_hess.data() : nullptr;
+}
+extern "C" int nlp_hess_l_work(long long* sz_arg, long long* sz_res, long long* sz_iw, long long* sz_w) {
+  if (sz_arg) *sz_arg = 4;
+  if (sz_res) *sz_res = 1;
+  if (sz_iw) *sz_iw = 0;
+  if (sz_w) *sz_w = 0;
+  return 0;
+}
+extern "C" int nlp_hess_l_alloc_mem(void) { return 0; }
+extern "C" int nlp_hess_l_init_mem(int) { return 0; }
+extern "C" void nlp_hess_l_free_mem(int) {}
+extern "C" int nlp_hess_l_checkout(void) { return 0; }
+extern "C" void nlp_hess_l_release(int) {}
+extern "C" void nlp_hess_l_incref(void) {}
+extern "C" void nlp_hess_l_decref(void) {}

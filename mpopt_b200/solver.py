@@ -4,8 +4,9 @@ The reference hands a symbolic NLP to ``ca.nlpsol(name, "ipopt", ...)`` (/root/r
 calls the returned object as ``solver(x0=, p=, lbx=, ubx=, lbg=, ubg=, lam_x0=, lam_g0=)`` getting the dict
 ``{x, f, g, lam_x, lam_g, lam_p}`` back (:804).  CasADi and IPOPT are not installed in this image, so:
 
-* ``ScipyNlpSolver`` -- the default here: SciPy SLSQP (small problems) or trust-constr (sparse) driving
-  ``Transcription.f / grad_f / g / jac_g``;  same call signature and result keys.
+* ``ScipyNlpSolver`` -- the default here: SciPy SLSQP (small problems) or trust-constr (sparse, exact Lagrangian
+  Hessian from ``Transcription.hess_l``) driving ``Transcription.f / grad_f / g / jac_g``;  same call signature and
+  result keys.
 * ``casadi_callbacks`` -- when ``import casadi`` succeeds, wraps the evaluators as ``ca.Callback`` objects with the
   Jacobian sparsity declared, ready for ``ca.nlpsol`` (untested here: no CasADi in the image).
 
@@ -63,8 +64,21 @@ class ScipyNlpSolver:
                               options={"maxiter": max_iter, "ftol": float(self.options.get("tol", 1e-10))})
             lam_g = np.zeros(n_g)
         else:
-            nlc = so.NonlinearConstraint(lambda z: gj(z)[0], lbg, ubg, jac=lambda z: gj(z)[1], hess=so.BFGS())
-            res = so.minimize(fobj, x0, jac=fgrad, hess=so.BFGS(), bounds=so.Bounds(lbx, ubx, keep_feasible=False),
+            # exact second derivatives from the Hessian kernel (CasADi's nlp_hess_l) unless the caller asks for a
+            # quasi-Newton model with IPOPT's option name
+            exact = self.options.get("ipopt.hessian_approximation", self.options.get("hessian_approximation", "exact")) == "exact"
+            if exact:
+                zero_lam = np.zeros(n_g)
+
+                def full(Hl):  # lower triangle -> symmetric
+                    return (Hl + sp.tril(Hl, k=-1).T).tocsr()
+
+                h_obj = lambda z: full(tr.hess_l(z, p, 1.0, zero_lam))
+                h_con = lambda z, v: full(tr.hess_l(z, p, 0.0, v))
+            else:
+                h_obj, h_con = so.BFGS(), so.BFGS()
+            nlc = so.NonlinearConstraint(lambda z: gj(z)[0], lbg, ubg, jac=lambda z: gj(z)[1], hess=h_con)
+            res = so.minimize(fobj, x0, jac=fgrad, hess=h_obj, bounds=so.Bounds(lbx, ubx, keep_feasible=False),
                               constraints=[nlc], method="trust-constr",
                               options={"maxiter": max_iter, "gtol": float(self.options.get("tol", 1e-8)),
                                        "xtol": 1e-12, "sparse_jacobian": True, "verbose": 0})

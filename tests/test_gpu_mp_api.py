@@ -151,3 +151,18 @@ def test_van_der_pol_solve(mp):
     mpo = mp.mpopt(van_der_pol(), 1, 15, "CGL")
     sol = mpo.solve()
     assert abs(sol["f"] - 2.8735) < 2e-2
+
+
+def test_trust_constr_with_exact_hessian(mp):
+    """The sparse solver path (trust-constr) fed by the Hessian kernel reaches the same optima as the reference's
+    IPOPT runs: moon lander 8.2477 (moon_lander.ipynb:185); and it needs fewer iterations than with a BFGS model."""
+    from mpopt_b200.problems import moon_lander
+
+    mpo = mp.mpopt(moon_lander(), 10, 4, "LGR")
+    sol = mpo.solve(nlp_solver_options={"method": "trust-constr", "max_iter": 400, "tol": 1e-8})
+    it_exact = mpo.nlp_solver.stats["iter_count"]
+    assert abs(sol["f"] - 8.2477) < 5e-2, (sol["f"], mpo.nlp_solver.stats)
+    mpo2 = mp.mpopt(moon_lander(), 10, 4, "LGR")
+    sol2 = mpo2.solve(nlp_solver_options={"method": "trust-constr", "max_iter": 400, "tol": 1e-8,
+                                          "hessian_approximation": "limited-memory"})
+    assert it_exact <= mpo2.nlp_solver.stats["iter_count"], (it_exact, mpo2.nlp_solver.stats)

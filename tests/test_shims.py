@@ -80,6 +80,17 @@ def test_ipopt_callbacks_match_oracle(libmpx):
     assert_close(grad, ora.grad_f(z, w), "grad_f")
     assert_close(g, ora.g(z, w), "g")
     assert_close(vals, J.data, "jac_g values")
+    # Eval_H_CB: pattern request, then values
+    from oracle.hessian import hess_l
+
+    lam = np.random.default_rng(1).uniform(-1, 1, m)
+    H = hess_l(ora, z, w, 0.8, lam)
+    nh = H.nnz
+    hr, hc, hv = np.zeros(nh, np.int32), np.zeros(nh, np.int32), np.zeros(nh)
+    assert libmpx.mpx_ipopt_eval_h(n, _lib.ptr(z), 0, 0.8, m, _lib.ptr(lam), 1, nh, ip(hr), ip(hc), None, ud) == 1
+    assert np.array_equal(hc, H.indices) and np.array_equal(hr, np.repeat(np.arange(n), np.diff(H.indptr)))
+    assert libmpx.mpx_ipopt_eval_h(n, _lib.ptr(z), 0, 0.8, m, _lib.ptr(lam), 1, nh, None, None, _lib.ptr(hv), ud) == 1
+    assert_close(hv, H.data, "eval_h values")
     # a new point
     z2 = z + 1e-3
     assert libmpx.mpx_ipopt_eval_g(n, _lib.ptr(z2), 1, m, _lib.ptr(g), ud) == 1
@@ -128,5 +139,21 @@ def test_casadi_externals_match_oracle(libmpx):
         res1 = (C.POINTER(C.c_double) * 1)(_lib.ptr(f))
         assert libmpx.nlp_f(arg, res1, None, None, 0) == 0
         assert abs(f[0] - ora.f(z, w)) <= 1e-10 * max(1.0, abs(ora.f(z, w)))
+        # nlp_hess_l (x, p, lam_f, lam_g) -> triu in CCS == the oracle's tril in CSR
+        from oracle.hessian import hess_l
+
+        lam, lf = np.random.default_rng(2).uniform(-1, 1, m), np.array([0.9])
+        H = hess_l(ora, z, w, 0.9, lam)
+        libmpx.nlp_hess_l_sparsity_out.restype = C.POINTER(C.c_longlong)
+        libmpx.nlp_hess_l_sparsity_out.argtypes = [C.c_longlong]
+        sph = libmpx.nlp_hess_l_sparsity_out(0)
+        assert (sph[0], sph[1]) == (n, n)
+        assert np.array_equal(np.array([sph[2 + i] for i in range(n + 1)]), H.indptr)
+        assert np.array_equal(np.array([sph[3 + n + i] for i in range(H.nnz)]), H.indices)
+        hv = np.zeros(H.nnz)
+        arg4 = (C.POINTER(C.c_double) * 4)(_lib.ptr(z), _lib.ptr(w), _lib.ptr(lf), _lib.ptr(lam))
+        res1 = (C.POINTER(C.c_double) * 1)(_lib.ptr(hv))
+        assert libmpx.nlp_hess_l(arg4, res1, None, None, 0) == 0
+        assert_close(hv, H.data, "nlp_hess_l")
     finally:
         libmpx.mpx_casadi_bind(None)
