@@ -158,11 +158,11 @@ def test_trust_constr_with_exact_hessian(mp):
     IPOPT runs: moon lander 8.2477 (moon_lander.ipynb:185); and it needs fewer iterations than with a BFGS model."""
     from mpopt_b200.problems import moon_lander
 
-    mpo = mp.mpopt(moon_lander(), 10, 4, "LGR")
-    sol = mpo.solve(nlp_solver_options={"method": "trust-constr", "max_iter": 400, "tol": 1e-8})
+    mpo = mp.mpopt(moon_lander(), 8, 3, "LGR")
+    sol = mpo.solve(nlp_solver_options={"method": "trust-constr", "max_iter": 300, "tol": 1e-8})
     it_exact = mpo.nlp_solver.stats["iter_count"]
     assert abs(sol["f"] - 8.2477) < 5e-2, (sol["f"], mpo.nlp_solver.stats)
-    mpo2 = mp.mpopt(moon_lander(), 10, 4, "LGR")
-    sol2 = mpo2.solve(nlp_solver_options={"method": "trust-constr", "max_iter": 400, "tol": 1e-8,
+    mpo2 = mp.mpopt(moon_lander(), 8, 3, "LGR")
+    sol2 = mpo2.solve(nlp_solver_options={"method": "trust-constr", "max_iter": 300, "tol": 1e-8,
                                           "hessian_approximation": "limited-memory"})
     assert it_exact <= mpo2.nlp_solver.stats["iter_count"], (it_exact, mpo2.nlp_solver.stats)

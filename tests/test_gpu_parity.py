@@ -26,6 +26,9 @@ CASES = [
     ("sink", "kitchen_sink", 7, [3, 4, 6, 2, 5, 4, 1], "LGL", True),
     ("sink_p1", "kitchen_sink", 4, 1, "LGR", False),
     ("p30_single", "moon_lander", 1, 30, "CGL", False),
+    ("hyper_p50", "hyper_sensitive", 5, 50, "LGR", False),   # docs/source/notebooks/hypersensitive.ipynb:165-170 (v1 kernel: degree > 31)
+    ("vdp_p25", "van_der_pol", 1, 25, "LGR", False),          # vanderpol.ipynb:177-182
+    ("moon_p40_mixed", "moon_lander", 3, [40, 6, 33], "LGL", True),
 ]
 
 
@@ -345,7 +348,8 @@ def test_peer_stores_replicate_every_output():
 
 
 @pytest.mark.parametrize("problem,K,po,scheme", [("van_der_pol", 5, [3, 6, 4, 9, 2], "LGR"), ("synthetic_6_3", 4, 15, "LGL"),
-                                                 ("two_phase_schwartz", 3, 7, "CGL"), ("kitchen_sink", 4, [4, 3, 5, 4], "LGR")])
+                                                 ("two_phase_schwartz", 3, 7, "CGL"), ("kitchen_sink", 4, [4, 3, 5, 4], "LGR"),
+                                                 ("hyper_sensitive", 2, [40, 12], "LGR")])
 def test_interpolation_and_residuals_match_oracle(libmpx, problem, K, po, scheme):
     """interpolation of a solution and the dynamics residual at arbitrary per-segment points
     (mpx_eval_residuals) against the oracle's restatement of mpopt.py:1428-1542, ragged and empty segments included."""
@@ -378,7 +382,8 @@ def test_interpolation_and_residuals_match_oracle(libmpx, problem, K, po, scheme
 @pytest.mark.parametrize("problem,K,po,scheme", [("moon_lander", 6, 4, "LGR"), ("kitchen_sink", 5, [3, 2, 4, 5, 3], "LGL"),
                                                  ("two_phase_schwartz", 4, 6, "LGR"), ("van_der_pol", 3, [2, 5, 3], "CGL"),
                                                  ("robot_arm", 7, 5, "LGR"), ("synthetic_6_3", 33, 15, "LGR"),
-                                                 ("hyper_sensitive", 3, 9, "LGL"), ("generic_two_phase", 3, [2, 5, 3], "CGL")])
+                                                 ("hyper_sensitive", 3, 9, "LGL"), ("generic_two_phase", 3, [2, 5, 3], "CGL"),
+                                                 ("hyper_sensitive", 2, [40, 7], "LGR")])
 def test_lagrangian_hessian_matches_oracle(libmpx, problem, K, po, scheme):
     """nlp_hess_l(x, p, lam_f, lam_g) -- lower triangle, CSR -- against the oracle's second-order
     dual-number restatement: pattern bit-exact, values to 1e-10."""
