@@ -123,15 +123,40 @@ __global__ void mpx_compact_kernel(const double* __restrict__ full, const int64_
 }
 
 // exclusive prefix sum of the segment widths of every phase (time grid, mpopt.py:192)
-__global__ void mpx_scan_widths_kernel(const double* w, double* sig0, int K) {
+#define MPX_SCAN_THREADS 1024
+__global__ void __launch_bounds__(MPX_SCAN_THREADS) mpx_scan_widths_kernel(const double* w, double* sig0, int K) {
+  // block-wide scan, one CTA per phase: every thread sums a contiguous chunk, the chunk totals are scanned with
+  // shuffles (fixed association, so the result is deterministic), then each thread writes its chunk's prefixes
+  __shared__ double wsum[MPX_SCAN_THREADS / 32];
   const double* wp = w + (int64_t)blockIdx.x * K;
   double* sp = sig0 + (int64_t)blockIdx.x * K;
-  if (threadIdx.x == 0) {
-    double acc = 0.0;
-    for (int k = 0; k < K; ++k) {
-      sp[k] = acc;
-      acc += wp[k];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int chunk = (K + MPX_SCAN_THREADS - 1) / MPX_SCAN_THREADS;
+  const int k0 = min(tid * chunk, K), k1 = min(k0 + chunk, K);
+  double s = 0.0;
+  for (int k = k0; k < k1; ++k) s += wp[k];
+  double incl = s;
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  double excl = __shfl_up_sync(0xffffffffu, incl, 1);  // exclusive prefix of this thread's chunk within its warp
+  if (lane == 0) excl = 0.0;
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    double v = wsum[lane];
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
     }
+    wsum[lane] = v;  // inclusive totals of the warps
+  }
+  __syncthreads();
+  double acc = excl + (warp > 0 ? wsum[warp - 1] : 0.0);
+  for (int k = k0; k < k1; ++k) {
+    sp[k] = acc;
+    acc += wp[k];
   }
 }
 
@@ -204,8 +229,8 @@ struct mpx_plan {
   bool hess_built = false;
   std::vector<int64_t> h_rowptr, h_colind;
   struct HessPhase {
-    DevBuf pos_yy, pos_ay, pos_ty, pos_corner, pos_term, term_assign, part;
-    int blocks = 0, n_corner = 0;
+    DevBuf pos_yy, pos_ay, pos_ty, pos_corner, pos_term, term_assign, part, lin;
+    int blocks = 0, n_corner = 0, affine = 0;
   };
   std::vector<HessPhase> hess_ph;
   DevBuf d_node_seg, d_lam, d_hvals;
@@ -445,7 +470,7 @@ struct MpxRtPhase final : MpxPhaseKernels {
   }
   cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
     cudaError_t e = go(f_hess[0], a, grid, MPX_HESS_THREADS, 0, st);
-    return e != cudaSuccess ? e : go(f_hess[1], a, 1, 64, 0, st);
+    return e != cudaSuccess ? e : go(f_hess[1], a, 1, MPX_HESS_FINAL_THREADS, 0, st);
   }
 };
 
@@ -979,7 +1004,13 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   CUDA_TRY(p.d_vals.ensure((size_t)p.nnz * sizeof(double)));
   if (!p.gather.empty()) CUDA_TRY(p.d_full.ensure((size_t)p.nnz_full * sizeof(double)));
   CUDA_TRY(p.d_grad.ensure((size_t)p.n_z * sizeof(double)));
-  CUDA_TRY(p.d_partial.ensure((size_t)p.n_p * MPX_NPART * sizeof(double)));
+  CUDA_TRY(p.d_partial.ensure(((size_t)(p.N + MPX_THREADS - 1) / MPX_THREADS + 1) * p.P * MPX_NPART * sizeof(double)));
+  {
+    std::vector<int32_t> node_seg((size_t)p.N, 0);
+    for (int k = 0; k < K; ++k)
+      for (int j = (k == 0 ? 0 : 1); j <= p.po[k]; ++j) node_seg[(size_t)p.seg_start[k] + j] = k;  // shared node: earlier segment
+    CUDA_TRY(up(p.d_node_seg, node_seg.data(), node_seg.size() * sizeof(int32_t)));
+  }
   CUDA_TRY(p.d_f.ensure(sizeof(double)));
 
   // ---- shared-memory budget (same formulas as the kernels)
@@ -1278,7 +1309,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
   bool need_sig = false;
   for (auto& L : p.ph) need_sig |= L.uses_t;
   if (need_sig) {
-    mpx_scan_widths_kernel<<<p.P, 32, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
+    mpx_scan_widths_kernel<<<p.P, MPX_SCAN_THREADS, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
     ++p.launches;
   }
   for (int ph = 0; ph < p.P; ++ph) {
@@ -1339,14 +1370,18 @@ static int launch_f_grad(mpx_plan& p, const double* d_z, const double* d_p, doub
   bool need_sig = false;
   for (auto& L : p.ph) need_sig |= L.cost_t;
   if (need_sig) {
-    mpx_scan_widths_kernel<<<p.P, 32, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
+    mpx_scan_widths_kernel<<<p.P, MPX_SCAN_THREADS, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
     ++p.launches;
   }
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs& a = p.args[ph];
     a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
-    a.grad = d_grad, a.partial = p.d_partial.as<double>() + (int64_t)ph * p.K * MPX_NPART, a.fout = d_f;
-    CUDA_TRY(p.prog->phases[ph]->fgrad(a, grad, grid, p.smem_fgrad, st));
+    a.node_begin = p.seg_begin == 0 ? 0 : p.seg_start[p.seg_begin] + 1, a.node_end = p.seg_start[p.seg_end] + 1;
+    a.f_blocks = (a.node_end - a.node_begin + MPX_THREADS - 1) / MPX_THREADS;
+    a.node_seg = p.d_node_seg.as<int32_t>();
+    a.grad = d_grad, a.partial = p.d_partial.as<double>() + (int64_t)ph * ((p.N + MPX_THREADS - 1) / MPX_THREADS + 1) * MPX_NPART;
+    a.fout = d_f;
+    CUDA_TRY(p.prog->phases[ph]->fgrad(a, grad, a.f_blocks, 0, st));
     CUDA_TRY(p.prog->phases[ph]->fgrad_final(a, grad, st));
     p.launches += 2;
   }
@@ -1587,6 +1622,22 @@ int build_hessian(mpx_plan& p) {
           const int64_t pos = pos_of(std::max(ca, cb), std::min(ca, cb));
           pterm.push_back(pos), tassign.push_back(owned[pos] ? 0 : 1);
         }
+    // rows of interior nodes are regular: position = base + i * stride (checked, not assumed)
+    std::vector<int64_t> lin;
+    bool affine = N >= 4;
+    auto add_lin = [&](const std::vector<int64_t>& pos, size_t n_ent) {
+      for (size_t e = 0; e < n_ent && affine; ++e) {
+        const int64_t* q = pos.data() + e * (size_t)N;
+        const int64_t stride = q[2] - q[1], base = q[1] - stride;
+        for (int64_t i = 1; i < N - 1; ++i)
+          if (q[i] != base + i * stride) { affine = false; break; }
+        lin.push_back(base), lin.push_back(stride);
+      }
+    };
+    add_lin(pyy, pyy.size() / (size_t)N), add_lin(pay, pay.size() / (size_t)N), add_lin(pty, 2 * nty);
+    H.affine = affine ? 1 : 0;
+    if (!affine) lin.assign(2, 0);
+    CUDA_TRY(upload(H.lin, lin.data(), lin.size() * sizeof(int64_t)));
     CUDA_TRY(upload(H.pos_yy, pyy.data(), pyy.size() * sizeof(int64_t)));
     CUDA_TRY(upload(H.pos_ay, pay.data(), pay.size() * sizeof(int64_t)));
     CUDA_TRY(upload(H.pos_ty, pty.data(), pty.size() * sizeof(int64_t)));
@@ -1596,10 +1647,6 @@ int build_hessian(mpx_plan& p) {
     H.blocks = (N + MPX_HESS_THREADS - 1) / MPX_HESS_THREADS, H.n_corner = n_corner;
     CUDA_TRY(H.part.ensure((size_t)H.blocks * n_corner * sizeof(double)));
   }
-  std::vector<int32_t> node_seg((size_t)N, 0);
-  for (int k = 0; k < p.K; ++k)
-    for (int j = (k == 0 ? 0 : 1); j <= p.po[k]; ++j) node_seg[(size_t)p.seg_start[k] + j] = k;  // shared node: earlier segment
-  CUDA_TRY(upload(p.d_node_seg, node_seg.data(), node_seg.size() * sizeof(int32_t)));
   CUDA_TRY(p.d_lam.ensure((size_t)p.n_g * sizeof(double)));
   CUDA_TRY(p.d_hvals.ensure(p.h_colind.size() * sizeof(double)));
   p.hess_built = true;
@@ -1608,7 +1655,7 @@ int build_hessian(mpx_plan& p) {
 
 int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f, const double* d_lam, double* d_vals,
                 cudaStream_t st) {
-  mpx_scan_widths_kernel<<<p.P, 32, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
+  mpx_scan_widths_kernel<<<p.P, MPX_SCAN_THREADS, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
   ++p.launches;
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs a = p.args[ph];
@@ -1617,6 +1664,7 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
     a.lam = d_lam, a.lam_f = lam_f, a.node_seg = p.d_node_seg.as<int32_t>();
     a.hp_yy = H.pos_yy.as<int64_t>(), a.hp_ay = H.pos_ay.as<int64_t>(), a.hp_ty = H.pos_ty.as<int64_t>();
     a.hp_corner = H.pos_corner.as<int64_t>(), a.hp_term = H.pos_term.as<int64_t>();
+    a.hp_lin = H.lin.as<int64_t>(), a.h_affine = H.affine;
     a.hp_term_assign = H.term_assign.as<int32_t>();
     a.hvals = d_vals, a.hpart = H.part.as<double>(), a.h_blocks = H.blocks;
     CUDA_TRY(p.prog->phases[ph]->hess(a, H.blocks, st));
@@ -1681,7 +1729,7 @@ extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw
   CUDA_TRY(dout.ensure((size_t)n_points * per * sizeof(double)));
   CUDA_TRY(cudaMemcpyAsync(dseg.p, seg, (size_t)n_points * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream));
   CUDA_TRY(cudaMemcpyAsync(dtau.p, taus, (size_t)n_points * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-  mpx_scan_widths_kernel<<<p->P, 32, 0, p->stream>>>(p->d_p.as<double>(), p->d_sig0.as<double>(), p->K);
+  mpx_scan_widths_kernel<<<p->P, MPX_SCAN_THREADS, 0, p->stream>>>(p->d_p.as<double>(), p->d_sig0.as<double>(), p->K);
   ++p->launches;
   MpxPhaseArgs a = p->args[phase];
   a.z = p->d_z.as<double>(), a.w = p->d_p.as<double>() + (int64_t)phase * p->K;

@@ -146,7 +146,7 @@ struct MpxAotPhase final : MpxPhaseKernels {
   }
   cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
     mpx_hess_kernel<PH><<<grid, MPX_HESS_THREADS, 0, st>>>(a);
-    mpx_hess_final<PH><<<1, 64, 0, st>>>(a);
+    mpx_hess_final<PH><<<1, MPX_HESS_FINAL_THREADS, 0, st>>>(a);
     return cudaGetLastError();
   }
 };

@@ -1,0 +1,53 @@
+"""Device time of every evaluator of the headline NLP (synthetic 6/3, K=4096, p=15, LGR), CUDA events around 100
+back-to-back calls with device-resident inputs.  Context for profiles/README.md; the bench metric is g + jac_g only."""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from mpopt_b200 import _lib  # noqa: E402
+from mpopt_b200.nlp import Transcription  # noqa: E402
+from mpopt_b200.problems import synthetic_6_3  # noqa: E402
+
+tr = Transcription(synthetic_6_3(), 4096, 15, "LGR")
+dev = torch.device("cuda", 0)
+stream = torch.cuda.Stream()
+torch.cuda.set_stream(stream)
+sp = stream.cuda_stream
+rng = np.random.default_rng(0)
+z = rng.uniform(-1, 1, tr.n_z)
+z[-2:] = [0.0, 1.0]
+zd = torch.from_numpy(z).to(dev)
+pd = torch.from_numpy(rng.dirichlet(np.ones(4096))).to(dev)
+lam = torch.from_numpy(rng.uniform(-1, 1, tr.n_g)).to(dev)
+g = torch.empty(tr.n_g, dtype=torch.float64, device=dev)
+v = torch.empty(tr.nnz, dtype=torch.float64, device=dev)
+grad = torch.empty(tr.n_z, dtype=torch.float64, device=dev)
+f = torch.empty(1, dtype=torch.float64, device=dev)
+nh = len(tr.hess_structure()[1])
+hv = torch.empty(nh, dtype=torch.float64, device=dev)
+L = _lib.lib()
+calls = {
+    "g + jac_g (mpx_eval_g_jac_dev)": (lambda: tr.g_jac_dev(zd.data_ptr(), pd.data_ptr(), g.data_ptr(), v.data_ptr(), sp), 8 * (tr.n_z + tr.n_p + tr.n_g + tr.nnz)),
+    "g only": (lambda: tr.g_jac_dev(zd.data_ptr(), pd.data_ptr(), g.data_ptr(), None, sp), 8 * (tr.n_z + tr.n_p + tr.n_g)),
+    "f + grad_f (mpx_eval_f_grad_dev)": (lambda: tr.f_grad_dev(zd.data_ptr(), pd.data_ptr(), f.data_ptr(), grad.data_ptr(), sp), 8 * (2 * tr.n_z + tr.n_p)),
+    "hess_l (mpx_eval_hess_l_dev)": (lambda: _lib.check(L.mpx_eval_hess_l_dev(tr._plan, zd.data_ptr(), pd.data_ptr(), C.c_double(0.7), lam.data_ptr(), hv.data_ptr(), sp)), 8 * (tr.n_z + tr.n_p + tr.n_g + 2 * nh)),
+}
+for name, (fn, nbytes) in calls.items():
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(100):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 10
+    print(json.dumps({"evaluator": name, "us": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2), "GBs": round(nbytes / us / 1e3, 1)}))
+print(json.dumps({"nnz_jac": tr.nnz, "nnz_hess_lower": nh}))
