@@ -306,8 +306,50 @@ class post_process:
         return tuple(np.vstack([p[i] for p in parts]) if i < 3 else np.concatenate([np.atleast_1d(p[i]) for p in parts])
                      for i in range(4))
 
+    _INTERPOLATION_NODES_PER_SEG = 50
+
+    def get_interpolation_taus(self, n: int = 75, taus_orig=None, method: str = "uniform"):
+        """mpopt.py:1690-1709."""
+        tr = self.mpo.transcription
+        if method == "uniform" or taus_orig is None:
+            return np.linspace(tr.tau0, tr.tau1, n)
+        return self.get_non_uniform_interpolation_grid(taus_orig, n)
+
+    @staticmethod
+    def get_non_uniform_interpolation_grid(taus_orig, n: int = 75):
+        """Insert mid-points until the grid has n points, at most six passes (mpopt.py:1711-1738)."""
+        taus = np.asarray(taus_orig, dtype=float)
+        for _ in range(6):
+            if len(taus) >= n:
+                break
+            fine = np.empty(2 * len(taus) - 1)
+            fine[0::2], fine[1::2] = taus, 0.5 * (taus[:-1] + taus[1:])
+            taus = fine
+        return taus
+
+    def get_interpolated_data(self, phases, taus=[]):
+        """(x, u, t, a) on a finer grid: Lagrange interpolation inside every segment, evaluated by the residual
+        kernel on the GPU (mpopt.py:1767-1826; the reference multiplies with a dense composite matrix)."""
+        mpo = self.mpo
+        tr, o = mpo.transcription, mpo._ocp
+        if not len(taus):
+            taus = [self.get_interpolation_taus(n=self._INTERPOLATION_NODES_PER_SEG)[1:] for _ in tr.poly_orders]
+            taus[0] = np.append(tr.tau0, taus[0])
+        z = np.asarray(self.solution["x"], dtype=float).reshape(-1)
+        sw = np.asarray(getattr(mpo, "_nlp_sw_params", mpo.get_segment_width_parameters()), dtype=float)
+        xs, us, ts, As = [], [], [], []
+        for phase in phases:
+            r = tr.residuals(z, sw, phase, taus, derivatives=False)
+            t_orig = self.get_trajectories(phase)[2]
+            ts.append(np.asarray(mpopt.get_interpolated_time_grid(t_orig, taus, tr.poly_orders, tr.tau0, tr.tau1)).reshape(-1))
+            xs.append(r["xi"] if self.scaling else r["xi"] / o.scale_x)
+            us.append(r["ui"] if self.scaling else r["ui"] / o.scale_u)
+            As.append(np.atleast_1d(self.get_trajectories(phase)[3]))
+        return np.vstack(xs), np.vstack(us), np.hstack(ts), np.hstack(As)
+
     def get_data(self, phases=[], interpolate: bool = False):
-        return self.get_original_data(phases)
+        phases = phases or self.phases
+        return self.get_interpolated_data(phases) if interpolate else self.get_original_data(phases)
 
 
 def solve(ocp, n_segments=1, poly_orders=9, scheme="LGR", plot=False, solve_dict=dict(), residual_x=False,

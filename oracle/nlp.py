@@ -141,12 +141,43 @@ class OracleNLP:
         A = z[o0 + (nx + nu) * N + 2: o0 + self.nvar]
         return X, U, T0, TF, A
 
-    def _time_grid(self, ph, T0, TF, p):
+    def _widths(self, ph, z, p):
+        """(segment widths of the phase, their columns in z or None).  Base class: widths are the NLP parameters
+        ``p`` (mpopt.py:152, :631); oracle/adaptive.py makes them decision variables."""
+        return np.asarray(p, dtype=float)[ph * self.K: (ph + 1) * self.K], None
+
+    def _emit_width_cols(self, emit, grad_or_none, rows, seg, frac, coef_h, coef_t, wcols, T):
+        """d/dw entries of rows whose value is  c(h_k, t)  with h_k = T/delta * w_k and t = t0 + T * sigma,
+        sigma = sum_{m<k} w_m + w_k * frac:  coef_h = dc/dh * T/delta (or None), coef_t = dc/dt (or None).
+        ``frac < 0`` marks a point whose time folded to t0 (node 0, mpopt.py:198): no width dependence through t."""
+        if wcols is None:
+            return
+        seg = np.asarray(seg)
+        own = np.zeros(len(seg)) if coef_h is None else np.asarray(coef_h, float).copy()
+        has_t = coef_t is not None
+        if has_t:
+            live = frac >= 0
+            own = own + np.where(live, np.asarray(coef_t, float) * T * np.where(live, frac, 0.0), 0.0)
+        sel = np.ones(len(seg), bool) if coef_h is not None else (frac >= 0)
+        if grad_or_none is None:
+            emit(np.asarray(rows)[sel], wcols[seg[sel]], own[sel])
+        else:
+            np.add.at(grad_or_none, wcols[seg[sel]], own[sel])
+        if has_t:  # every earlier segment shifts the point's time by T per unit width
+            for i in np.nonzero(seg > 0)[0]:
+                m = np.arange(seg[i])
+                v = np.full(len(m), float(np.asarray(coef_t)[i]) * T)
+                if grad_or_none is None:
+                    emit(np.full(len(m), np.asarray(rows)[i]), wcols[m], v)
+                else:
+                    np.add.at(grad_or_none, wcols[m], v)
+
+    def _time_grid(self, ph, T0, TF, w):
         """h per node, t per node and d t/d tf (sigma) -- mpopt.py:175-198."""
         o = self.ocp
         st = o.scale_t
         t0, tf = T0 / st, TF / st  # :175-176
-        w = np.asarray(p, dtype=float)[ph * self.K: (ph + 1) * self.K]  # :152, :631
+        w = np.asarray(w, dtype=float)
         delta = self.tau1 - self.tau0
         h_seg = (tf - t0) / delta * w  # :184, :193-195
         # t_seg0 += h_seg*(tau1 - tau0), accumulated sequentially (:192)
@@ -186,9 +217,14 @@ class OracleNLP:
         R = self._rows[ph]
         st = o.scale_t
         X, U, T0, TF, A = self._unpack(ph, z)
-        h, t, sigma, dh = self._time_grid(ph, T0, TF, p)
+        w, wcols = self._widths(ph, z, p)
+        h, t, sigma, dh = self._time_grid(ph, T0, TF, w)
         x, u, td, a = self._node_inputs(ph, X, U, A, t)
         nodes = np.arange(N)
+        T = (TF - T0) / st
+        hw = T / (self.tau1 - self.tau0)                      # d h_k / d w_k
+        frac = self.node_dtau / (self.tau1 - self.tau0)       # d sigma_i / d w_k(i)
+        frac_t = np.where(nodes == 0, -1.0, frac)             # node 0: t folded to t0 (:198)
         g = np.zeros(R["n"])
         rows, cols, vals = [], [], []
         grad = np.zeros(self.n_z)
@@ -220,6 +256,8 @@ class OracleNLP:
             if nz:
                 emit(R["F"] + s * N + nodes, np.full(N, cTF), -dh * sx * fv - h * sx * ft * sigma / st)
                 emit(R["F"] + s * N + nodes, np.full(N, cT0), +dh * sx * fv - h * sx * ft * (1.0 - sigma) / st)
+                self._emit_width_cols(emit, None, R["F"] + s * N + nodes, self.node_seg, frac_t, -hw * sx * fv,
+                                      (-h * sx * ft) if ("t",) in fder else None, wcols, T)
 
         # ---------------- path constraints  C = vec(c)   (:204, :254-258)
         if R["nc"]:
@@ -236,6 +274,7 @@ class OracleNLP:
                         emit(r0 + nodes, np.full(N, cT0), d * (1.0 - sigma) / st)
                         # node 0: t = t0 + h*0.0 folds to t0 -> no TF dependence (:198)
                         emit(r0 + nodes[1:], np.full(N - 1, cTF), (d * sigma / st)[1:])
+                        self._emit_width_cols(emit, None, r0 + nodes, self.node_seg, frac_t, None, d, wcols, T)
                     else:
                         emit(r0 + nodes, self._col_of(ph, key, nodes), d)
 
@@ -308,10 +347,16 @@ class OracleNLP:
         if Lnz:
             grad[cTF] += float(W @ (dh * Lv + h * Lt * sigma / st))
             grad[cT0] += float(W @ (-dh * Lv + h * Lt * (1.0 - sigma) / st))
+            self._emit_width_cols(None, grad, nodes, self.node_seg, frac_t, W * hw * Lv,
+                                  (W * h * Lt) if ("t",) in Lder else None, wcols, T)
 
+        self._extra_rows(ph, R, g, emit if want_jac else None, X, U, T0, TF, A, w, wcols, t)
         trip = (np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)) if rows else (
             np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0))
         return g, J, trip, grad
+
+    def _extra_rows(self, ph, R, g, emit, X, U, T0, TF, A, w, wcols, t):
+        """Hook for subclasses that append constraint blocks to a phase (oracle/adaptive.py)."""
 
     def _events(self, z, want_jac=True):
         """Phase-link rows (mpopt.py:464-521), appended after all phases (:617-621)."""
