@@ -67,6 +67,9 @@ typedef struct mpx_phase_desc {
    * lower triangle used, row-major, variables (x.., u.., a.., t, h) resp. (xf.., x0.., tf, t0, a..) */
   const uint8_t* pat_hw;   /* [nv+2][nv+2]  node Lagrangian h (sw L - sum lamF Sx f) + sum lamC c     */
   const uint8_t* pat_ht;   /* [2nx+2+na][2nx+2+na]  sw M + sum lamT tc                                */
+  /* adaptive NLP only (mpx_problem_desc.adaptive): mid-point rows of the SW block, mpopt.py:3062-3082 */
+  int32_t sw_u;            /* any control bound finite: compI.U rows present                */
+  int32_t sw_x;            /* any state bound finite: compI.X rows present                  */
 } mpx_phase_desc;
 
 typedef struct mpx_problem_desc {
@@ -90,6 +93,12 @@ typedef struct mpx_problem_desc {
   int32_t seg_begin, seg_end;     /* shard: evaluate segments [seg_begin, seg_end) of every
                                      phase; 0,0 means all. Tail rows (terminal, events)
                                      belong to the shard that owns the last segment.       */
+  int32_t adaptive;               /* 1: the NLP of mpopt_adaptive (mpopt.py:2877-3375): the segment
+                                     widths are decision variables appended to every phase of z
+                                     ([X | U | t0 | tf | a | w], :2938-2945), n_p = 0, rows per phase
+                                     [F | C | DU | TC | SW] (:3169; midu / du_continuity are ignored).
+                                     Not available for shards, peers or the Hessian.       */
+  int32_t mid_residuals;          /* adaptive: mid-point residual rows present (:2918, :3084-3130) */
 } mpx_problem_desc;
 
 typedef struct mpx_plan mpx_plan;

@@ -23,7 +23,8 @@ c_f64p = C.POINTER(C.c_double)
 class PhaseDesc(C.Structure):
     _fields_ = [("n_path", C.c_int32), ("n_term", C.c_int32), ("pat_f", c_u8p), ("f_nz", c_u8p), ("f_t", c_u8p),
                 ("pat_c", c_u8p), ("c_t", c_u8p), ("pat_tc", c_u8p), ("diff_u", C.c_int32), ("midu", C.c_int32),
-                ("du_continuity", C.c_int32), ("cost_t", C.c_int32), ("pat_hw", c_u8p), ("pat_ht", c_u8p)]
+                ("du_continuity", C.c_int32), ("cost_t", C.c_int32), ("pat_hw", c_u8p), ("pat_ht", c_u8p),
+                ("sw_u", C.c_int32), ("sw_x", C.c_int32)]
 
 
 class ProblemDesc(C.Structure):
@@ -33,7 +34,7 @@ class ProblemDesc(C.Structure):
                 ("scale_u", c_f64p), ("scale_a", c_f64p), ("scale_t", C.c_double), ("n_links", C.c_int32),
                 ("links", c_i32p), ("drop_exact_zeros", C.c_int32), ("program_key", C.c_char_p),
                 ("program_source", C.c_char_p), ("device", C.c_int32), ("seg_begin", C.c_int32),
-                ("seg_end", C.c_int32)]
+                ("seg_end", C.c_int32), ("adaptive", C.c_int32), ("mid_residuals", C.c_int32)]
 
 
 class IpoptData(C.Structure):

@@ -256,3 +256,70 @@ class mpopt_h_adaptive(mpopt):
             w[n_head:n_head + n_avail - 1] = np.diff(cuts)
             w[n_head + n_avail - 1:] = tail / n_tail
         return w / (tf - t0)
+
+
+class mpopt_adaptive(mpopt):
+    """``mp.mpopt_adaptive``: the segment widths are decision variables of the NLP and are solved for together with the
+    trajectory (/root/reference/mpopt/mpopt.py:2877-3375).
+
+    Per phase ``z = [X, U, t0, tf, a, w_0 .. w_{K-1}]`` (:2938-2945), no NLP parameters (:3190-3191), rows
+    ``[F, C, DU, TC, SW]`` (:3169) with ``SW = [sum(w) - 1, compI.U, compI.X, mid-point residuals]`` (:3034-3136).
+    The same kernels evaluate ``F / C / DU / TC`` (they read the widths out of z); ``mpx_adapt_kernel`` adds the
+    ``SW`` block and every ``d/dw`` entry.  Set ``mid_residuals``, ``lbh``, ``ubh``, ``tol_residual`` before the first
+    ``solve`` / ``create_solver`` like in the reference (tests/test_mpopt.py:474)."""
+
+    _SEG_WIDTH_MIN = 1e-4
+    _SEG_WIDTH_MAX = 1.0
+    _TOL_RESIDUAL = 1e-3
+
+    def __init__(self, problem, n_segments: int = 1, poly_orders=[9], scheme: str = "LGR", **kwargs):
+        super().__init__(problem, n_segments=n_segments, poly_orders=poly_orders, scheme=scheme, **kwargs)
+        P = self._ocp.n_phases
+        self.mid_residuals = True
+        self.lbh = [self._SEG_WIDTH_MIN] * P
+        self.ubh = [self._SEG_WIDTH_MAX] * P
+        self.tol_residual = [self._TOL_RESIDUAL] * P
+
+    @property
+    def transcription(self):
+        if self._tr is None:
+            from .collocation import CollocationRoots
+            from .nlp import Transcription
+
+            tr = Transcription(self._ocp, self.n_segments, self.poly_orders, self.colloc_scheme,
+                               tau_min=float(CollocationRoots._TAU_MIN), tau_max=float(CollocationRoots._TAU_MAX),
+                               device=self.device, adaptive=True, mid_residuals=self.mid_residuals)
+            tr.lbh, tr.ubh, tr.tol_residual = list(self.lbh), list(self.ubh), list(self.tol_residual)
+            self._tr = tr
+            o = self._ocp
+            self._optimization_vars_per_phase = self._Npoints * (o.nx + o.nu) + o.na + 2 + self.n_segments
+            self._variables_created = True
+        return self._tr
+
+    def get_nlp_constrains_for_segment_widths(self, phase: int = 0):
+        """(SW, SWmin, SWmax): row indices and bounds of the width block of one phase (mpopt.py:3034-3136)."""
+        tr = self.transcription
+        _, _, gmin, gmax = tr.bounds()
+        a = tr.layout.phases[phase].gSW
+        b = tr.layout.phases[phase + 1].gF if phase + 1 < len(tr.layout.phases) else tr.layout.g_events
+        return np.arange(a, b), gmin[a:b], gmax[a:b]
+
+    def get_segment_width_parameters(self, solution=None):
+        return np.zeros(0)  # the NLP has no parameters (:3190-3191)
+
+    def create_solver(self, solver: str = "ipopt", options={}):
+        super().create_solver(solver=solver, options=options)
+
+    def solve(self, initial_solution=None, reinitialize_nlp=False, solver="ipopt", nlp_solver_options={},
+              mpopt_options={}, **kwargs):
+        """mpopt.py:3207-3246: solve, then read the optimal width fractions out of x."""
+        if (not self._nlpsolver_initialized) or reinitialize_nlp:
+            self.create_solver(solver=solver, options=nlp_solver_options)
+        inputs = self.get_solver_warm_start_input_parameters(initial_solution)
+        solution = self.nlp_solver(**inputs, **self.nlp_bounds)
+        L, K = self.transcription.layout, self.n_segments
+        x = np.asarray(solution["x"], dtype=float).reshape(-1)
+        self._nlp_sw_params = np.concatenate([x[L.colW(ph, 0): L.colW(ph, 0) + K] for ph in range(self._ocp.n_phases)])
+        if not self._MUTE_:
+            print(f"Optimal segment width fractions: {self._nlp_sw_params}")
+        return solution

@@ -124,11 +124,12 @@ __global__ void mpx_compact_kernel(const double* __restrict__ full, const int64_
 
 // exclusive prefix sum of the segment widths of every phase (time grid, mpopt.py:192)
 #define MPX_SCAN_THREADS 1024
-__global__ void __launch_bounds__(MPX_SCAN_THREADS) mpx_scan_widths_kernel(const double* w, double* sig0, int K) {
+__global__ void __launch_bounds__(MPX_SCAN_THREADS) mpx_scan_widths_kernel(const double* w, double* sig0, int K,
+                                                                           int64_t stride) {
   // block-wide scan, one CTA per phase: every thread sums a contiguous chunk, the chunk totals are scanned with
   // shuffles (fixed association, so the result is deterministic), then each thread writes its chunk's prefixes
   __shared__ double wsum[MPX_SCAN_THREADS / 32];
-  const double* wp = w + (int64_t)blockIdx.x * K;
+  const double* wp = w + (int64_t)blockIdx.x * stride;  // stride K: parameter vector; nvar: widths inside z (adaptive)
   double* sp = sig0 + (int64_t)blockIdx.x * K;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int chunk = (K + MPX_SCAN_THREADS - 1) / MPX_SCAN_THREADS;
@@ -172,11 +173,21 @@ struct PhaseLayout {
   int64_t vF[MPX_MAXS], vC[MPX_MAXS];
   int64_t vDU = 0, vmU = 0, vdU = 0, vTC = 0;
   bool uses_t = false, cost_t = false;
+  // adaptive NLP (mpopt_adaptive): SW block and the offsets of the entries mpx_adapt_kernel writes (into the ext section)
+  bool sw_u = false, sw_x = false;
+  int64_t gSW = 0, eSum = 0, eUi = 0, eXi = 0, eRes = 0;
+  int64_t eF[MPX_MAXS], eC[MPX_MAXS];
+  std::vector<int> res_nblk, res_na;  // per state: (d+1)-wide column blocks / parameter entries of a residual row
+  std::vector<int64_t> seg_rpre;      // [K] residual-row entries before the segment
 };
 
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr, o.bytes = 0; }
   ~DevBuf() {
     if (p) cudaFree(p);
   }
@@ -202,6 +213,12 @@ struct mpx_plan {
   std::vector<int> links;
   int seg_begin, seg_end;
   bool drop, uniform;
+  bool adaptive = false, mid_res = false;  // widths-as-variables NLP (mpopt.py:2877-3375)
+  int64_t n_base = 0, n_ext = 0;           // staged values: [base kernels | mpx_adapt_kernel]
+  std::vector<int> dmid_off;               // per unique degree: record offset in h_dmid
+  std::vector<double> h_dmid;              // D at the mid points, [d][d+1] per degree
+  DevBuf d_dmid, d_seg_dmid, d_wpart, d_seg_rpre;  // d_seg_rpre: [P][K]
+  int smem_adapt = 0;
   int64_t nvar, n_z, n_p, n_g, nnz_full, nnz;
   int64_t nnzD, nnzI, nnzS;
   int64_t g_events, v_events;
@@ -425,7 +442,8 @@ RtApi& rt_api() {
 // launches through the driver API; same interface as the AOT phases
 struct MpxRtPhase final : MpxPhaseKernels {
   CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_gjac4[2] = {nullptr, nullptr},
-               f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr}, f_resid[2] = {nullptr, nullptr}, f_hess[2] = {nullptr, nullptr};
+               f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr}, f_resid[2] = {nullptr, nullptr}, f_hess[2] = {nullptr, nullptr},
+               f_adapt[3] = {nullptr, nullptr, nullptr};
   static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st,
                         bool pdl = false) {
     RtApi& R = rt_api();
@@ -472,6 +490,13 @@ struct MpxRtPhase final : MpxPhaseKernels {
     cudaError_t e = go(f_hess[0], a, grid, MPX_HESS_THREADS, 0, st);
     return e != cudaSuccess ? e : go(f_hess[1], a, 1, MPX_HESS_FINAL_THREADS, 0, st);
   }
+  cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
+    return go(f_adapt[0], a, grid, MPX_THREADS, smem, st);
+  }
+  cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
+    cudaError_t e = go(f_adapt[1], a, grid, MPX_THREADS, 0, st);
+    return e != cudaSuccess ? e : go(f_adapt[2], a, 1, 32, 0, st);
+  }
 };
 
 struct RtProgram {
@@ -515,7 +540,8 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
                         (strcmp(k, "mpx_gjac4_kernel") == 0 || strcmp(k, "mpx_gjac2_kernel") == 0 ? ", 0>" : ">"));
   std::vector<std::string> names1;  // kernels with the phase functor as their only template argument
   for (int ph = 0; ph < n_phases; ++ph)
-    for (const char* k : {"mpx_hess_kernel", "mpx_hess_final"}) names1.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ">");
+    for (const char* k : {"mpx_hess_kernel", "mpx_hess_final", "mpx_adapt_kernel", "mpx_adapt_grad_kernel", "mpx_adapt_grad_suffix"})
+      names1.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ">");
   for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
   for (auto& nm : names1) R.AddNameExpression(prog, nm.c_str());
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
@@ -553,10 +579,11 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
           return fail(MPX_ECUDA, "kernel " + names[idx] + " not found in the run-time compiled module");
         }
       }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < 5; ++b) {
       const char* lowered = nullptr;
-      const std::string& nm = names1[(size_t)ph * 2 + b];
-      if (R.GetLoweredName(prog, nm.c_str(), &lowered) != 0 || !lowered || R.ModuleGetFunction(&P->f_hess[b], mod, lowered) != 0) {
+      const std::string& nm = names1[(size_t)ph * 5 + b];
+      CUfunction_t* slot = b < 2 ? &P->f_hess[b] : &P->f_adapt[b - 2];
+      if (R.GetLoweredName(prog, nm.c_str(), &lowered) != 0 || !lowered || R.ModuleGetFunction(slot, mod, lowered) != 0) {
         R.DestroyProgram(&prog);
         return fail(MPX_ECUDA, "kernel " + nm + " not found in the run-time compiled module");
       }
@@ -660,10 +687,18 @@ struct Builder {
   mpx_plan& P;
   std::vector<int64_t> rowptr, colind;
   std::vector<uint8_t> keep;
+  std::vector<int64_t> src;  // position of the entry in the staged value buffer the kernels write
+  int64_t n_base = 0;        // entries of the base kernels so far (their write order = the order of add())
   explicit Builder(mpx_plan& p) : P(p) { rowptr.push_back(0); }
   void add(int64_t col, bool k = true) {
     colind.push_back(col);
     keep.push_back(k ? 1 : 0);
+    src.push_back(n_base++);
+  }
+  void add_ext(int64_t col, int64_t ext_pos, bool k = true) {  // entry written by mpx_adapt_kernel
+    colind.push_back(col);
+    keep.push_back(k ? 1 : 0);
+    src.push_back(-1 - ext_pos);
   }
   void end_row() { rowptr.push_back((int64_t)colind.size()); }
 };
@@ -690,6 +725,7 @@ static void build_structure(mpx_plan& p) {
     auto colU = [&](int i, int c) { return zo + (int64_t)(nx + c) * N + i; };
     const int64_t cT0 = zo + (int64_t)(nx + nu) * N, cTF = cT0 + 1;
     auto colA = [&](int m) { return cT0 + 2 + m; };
+    auto colW = [&](int m) { return cT0 + 2 + na + m; };  // adaptive NLP only (mpopt.py:2938-2945)
     // F rows
     for (int s = 0; s < nx; ++s) {
       const uint8_t* pat = L.pat_f.data() + (size_t)s * nv;
@@ -710,6 +746,12 @@ static void build_structure(mpx_plan& p) {
         if (L.f_nz[s]) B.add(cT0), B.add(cTF);
         for (int m = 0; m < na; ++m)
           if (pat[nx + nu + m]) B.add(colA(m));
+        if (p.adaptive && L.f_nz[s]) {  // h_k = (tf - t0)/delta * w_k; t_i also moves with every earlier width
+          if (L.f_t[s])
+            for (int m = 0; m <= k; ++m) B.add_ext(colW(m), L.eF[s] + (int64_t)i * K + m);
+          else
+            B.add_ext(colW(k), L.eF[s] + i);
+        }
         B.end_row();
       }
     }
@@ -724,6 +766,8 @@ static void build_structure(mpx_plan& p) {
         if (L.c_t[q]) B.add(cT0), B.add(cTF, i != 0);  // node 0: t = t0 + h*0.0 folds to t0 (mpopt.py:198)
         for (int m = 0; m < na; ++m)
           if (pat[nx + nu + m]) B.add(colA(m));
+        if (p.adaptive && L.c_t[q] && i != 0)
+          for (int m = 0; m <= nseg[i]; ++m) B.add_ext(colW(m), L.eC[q] + (int64_t)i * K + m);
         B.end_row();
       }
     }
@@ -773,6 +817,58 @@ static void build_structure(mpx_plan& p) {
         if (pat[2 * nx + 2 + m]) B.add(colA(m));
       B.end_row();
     }
+    // SW block of the adaptive NLP (mpopt.py:3034-3136)
+    if (p.adaptive) {
+      for (int m = 0; m < K; ++m) B.add_ext(colW(m), L.eSum + m);
+      B.end_row();
+      for (int blk = 0; blk < 2; ++blk) {  // compI.U then compI.X
+        if (!(blk == 0 ? L.sw_u : L.sw_x)) continue;
+        const int nvv = blk == 0 ? nu : nx;
+        for (int c = 0; c < nvv; ++c) {
+          int64_t pos = (blk == 0 ? L.eUi : L.eXi) + (int64_t)c * p.nnzI;
+          for (int k = 0; k < K; ++k) {
+            const int d = p.po[k], n1 = d + 1;
+            const double* C = tab_of(p, d) + MpxTab::off_C(n1);
+            for (int m = 0; m < d; ++m) {
+              for (int j = 0; j <= d; ++j, ++pos) {
+                const int64_t col = blk == 0 ? colU(p.seg_start[k] + j, c) : colX(p.seg_start[k] + j, c);
+                B.add_ext(col, pos, !(p.drop && C[m * n1 + j] == 0.0));
+              }
+              B.end_row();
+            }
+          }
+        }
+      }
+      if (p.mid_res) {
+        for (int k = 0; k < K; ++k) {
+          const int d = p.po[k], n1 = d + 1;
+          const double* DI = p.h_dmid.data() + p.dmid_off[std::lower_bound(p.degs.begin(), p.degs.end(), d) - p.degs.begin()];
+          int64_t pos = L.eRes + L.seg_rpre[k];
+          for (int s = 0; s < nx; ++s) {
+            const uint8_t* pat = L.pat_f.data() + (size_t)s * nv;
+            for (int m = 0; m < d; ++m) {
+              for (int v = 0; v < nx + nu; ++v) {
+                if (!(v == s || pat[v])) continue;
+                for (int j = 0; j <= d; ++j, ++pos) {
+                  const int64_t col = v < nx ? colX(p.seg_start[k] + j, v) : colU(p.seg_start[k] + j, v - nx);
+                  B.add_ext(col, pos, !(p.drop && v == s && !pat[s] && DI[m * n1 + j] == 0.0));
+                }
+              }
+              if (L.f_nz[s]) B.add_ext(cT0, pos++), B.add_ext(cTF, pos++);
+              for (int m2 = 0; m2 < na; ++m2)
+                if (pat[nx + nu + m2]) B.add_ext(colA(m2), pos++);
+              if (L.f_t[s]) {
+                for (int m2 = 0; m2 < K; ++m2, ++pos)
+                  if (m2 <= k) B.add_ext(colW(m2), pos);
+              } else {
+                B.add_ext(colW(k), pos++);
+              }
+              B.end_row();
+            }
+          }
+        }
+      }
+    }
   }
   // event rows: state block, control block, time block (mpopt.py:484-519)
   const int nl = (int)p.links.size() / 2;
@@ -798,8 +894,11 @@ static void build_structure(mpx_plan& p) {
     cudaMemcpy(p.d_evcols.p, both.data(), both.size() * sizeof(int64_t), cudaMemcpyHostToDevice);
   }
   // compact
-  p.nnz_full = (int64_t)B.colind.size();
-  bool all = true;
+  p.n_base = B.n_base;
+  p.nnz_full = p.n_base + p.n_ext;
+  for (int64_t& v : B.src)
+    if (v < 0) v = p.n_base + (-1 - v);  // ext section follows the base kernels' entries
+  bool all = !p.adaptive;
   for (uint8_t k : B.keep)
     if (!k) {
       all = false;
@@ -815,7 +914,7 @@ static void build_structure(mpx_plan& p) {
     p.gather.clear();
     for (size_t r = 0; r + 1 < B.rowptr.size(); ++r) {
       for (int64_t e = B.rowptr[r]; e < B.rowptr[r + 1]; ++e)
-        if (B.keep[e]) p.colind.push_back(B.colind[e]), p.gather.push_back(e);
+        if (B.keep[e]) p.colind.push_back(B.colind[e]), p.gather.push_back(B.src[e]);
       p.rowptr.push_back((int64_t)p.colind.size());
     }
   }
@@ -863,6 +962,9 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   if (p.st == 0.0) return fail(MPX_EINVAL, "scale_t must be non-zero");
   p.seg_begin = d->seg_begin, p.seg_end = d->seg_end;
   if (p.seg_begin == 0 && p.seg_end == 0) p.seg_end = p.K;
+  p.adaptive = d->adaptive != 0, p.mid_res = p.adaptive && d->mid_residuals != 0;
+  if (p.adaptive && !(p.seg_begin == 0 && p.seg_end == p.K))
+    return fail(MPX_EINVAL, "the adaptive NLP (widths as variables) cannot be sharded: its rows couple all segments");
   if (p.seg_begin < 0 || p.seg_end > p.K || p.seg_begin >= p.seg_end) return fail(MPX_EINVAL, "bad segment shard");
   if (d->n_links < 0 || (d->n_links && !d->links)) return fail(MPX_EINVAL, "bad phase links");
   p.links.assign(d->links, d->links + 2 * d->n_links);
@@ -890,9 +992,9 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
 
   // ---- sizes and offsets
   const int nx = p.nx, nu = p.nu, na = p.na, N = p.N, K = p.K, nv = nx + nu + na;
-  p.nvar = (int64_t)N * (nx + nu) + 2 + na;
+  p.nvar = (int64_t)N * (nx + nu) + 2 + na + (p.adaptive ? K : 0);  // adaptive: widths appended (mpopt.py:2938-2945)
   p.n_z = p.nvar * p.P;
-  p.n_p = (int64_t)K * p.P;
+  p.n_p = p.adaptive ? 0 : (int64_t)K * p.P;                        // :3190-3191
   p.nnzD = (int64_t)(p.po[0] + 1) * (p.po[0] + 1);
   p.nnzI = 0, p.nnzS = 0;
   for (int k = 0; k < K; ++k) {
@@ -917,6 +1019,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     copy_pat(L.pat_hw, q.pat_hw, (size_t)(nv + 2) * (nv + 2));
     copy_pat(L.pat_ht, q.pat_ht, (size_t)(2 * nx + 2 + na) * (2 * nx + 2 + na));
     L.has_DU = q.diff_u != 0, L.has_mU = q.midu != 0, L.has_dU = q.du_continuity != 0 && K > 1;
+    if (p.adaptive) L.has_mU = L.has_dU = false, L.sw_u = q.sw_u != 0, L.sw_x = q.sw_x != 0;  // rows [F C DU TC SW], :3169
     L.zoff = p.nvar * ph;
     L.cost_t = q.cost_t != 0;
     L.f_next.assign(nx, 0), L.c_len.assign(L.nc, 0), L.tc_len.assign(L.ntc, 0);
@@ -941,6 +1044,40 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     L.gmU = row, row += L.has_mU ? (int64_t)nu * (N - 1) : 0;
     L.gdU = row, row += L.has_dU ? (int64_t)nu * (K - 1) : 0;
     L.gTC = row, row += L.ntc;
+    if (p.adaptive) {
+      L.gSW = row;
+      row += 1 + (L.sw_u ? (int64_t)nu * (N - 1) : 0) + (L.sw_x ? (int64_t)nx * (N - 1) : 0) +
+             (p.mid_res ? (int64_t)nx * (N - 1) : 0);
+      // ext section: what mpx_adapt_kernel writes, in its own regular layout
+      int64_t e = p.n_ext;
+      for (int s = 0; s < nx; ++s) {
+        L.eF[s] = L.f_nz[s] ? e : -1;
+        if (L.f_nz[s]) e += L.f_t[s] ? (int64_t)N * K : N;
+      }
+      for (int c = 0; c < L.nc; ++c) {
+        L.eC[c] = L.c_t[c] ? e : -1;
+        if (L.c_t[c]) e += (int64_t)N * K;
+      }
+      L.eSum = e, e += K;
+      L.eUi = e, e += L.sw_u ? (int64_t)nu * p.nnzI : 0;
+      L.eXi = e, e += L.sw_x ? (int64_t)nx * p.nnzI : 0;
+      L.eRes = e;
+      L.res_nblk.assign(nx, 0), L.res_na.assign(nx, 0), L.seg_rpre.assign(K, 0);
+      for (int s = 0; s < nx; ++s) {
+        for (int v = 0; v < nx + nu; ++v) L.res_nblk[s] += (v == s || L.pat_f[(size_t)s * nv + v]) ? 1 : 0;
+        for (int m = 0; m < na; ++m) L.res_na[s] += L.pat_f[(size_t)s * nv + nx + nu + m] ? 1 : 0;
+      }
+      if (p.mid_res) {
+        int64_t acc = 0;
+        for (int k = 0; k < K; ++k) {
+          L.seg_rpre[k] = acc;
+          for (int s = 0; s < nx; ++s)
+            acc += (int64_t)p.po[k] * ((int64_t)(p.po[k] + 1) * L.res_nblk[s] + 2 * L.f_nz[s] + L.res_na[s] + (L.f_t[s] ? K : 1));
+        }
+        e += acc;
+      }
+      p.n_ext = e;
+    }
     for (int s = 0; s < nx; ++s) L.vF[s] = val, val += p.nnzD + (int64_t)N * L.f_next[s];
     for (int c = 0; c < L.nc; ++c) L.vC[c] = val, val += (int64_t)N * L.c_len[c];
     L.vDU = val, val += L.has_DU ? (int64_t)nu * p.nnzD : 0;
@@ -993,13 +1130,53 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   CUDA_TRY(up(p.d_seg_ipre, ipre.data(), K * sizeof(int64_t)));
   CUDA_TRY(up(p.d_seg_spre, spre.data(), K * sizeof(int64_t)));
 
+  if (p.adaptive) {  // D at the mid points of every unique degree (mpopt.py:3055-3060), on the device like the other tables
+    int tot = 0;
+    for (int dg : p.degs) p.dmid_off.push_back(tot), tot += dg * (dg + 1);
+    p.h_dmid.resize(tot);
+    CUDA_TRY(p.d_dmid.ensure((size_t)tot * sizeof(double)));
+    for (size_t i = 0; i < p.degs.size(); ++i) {
+      const int dg = p.degs[i], n1 = dg + 1;
+      const double* R = p.h_tabs.data() + p.rec_off[i] + MpxTab::off_roots(n1);
+      std::vector<double> mid(dg);
+      for (int m = 0; m < dg; ++m) mid[m] = (R[m] + R[m + 1]) / 2.0;  // :3040-3046
+      DevBuf dt;
+      CUDA_TRY(dt.ensure(dg * sizeof(double)));
+      CUDA_TRY(cudaMemcpy(dt.p, mid.data(), dg * sizeof(double), cudaMemcpyHostToDevice));
+      mpx_basis_at_kernel<<<1, MPX_TAB_THREADS, (size_t)(n1 + 2) * sizeof(double), p.stream>>>(
+          p.scheme, dg, p.tau_min, p.tau_max, 1, dg, dt.as<double>(), p.d_dmid.as<double>() + p.dmid_off[i]);
+      CUDA_TRY(cudaGetLastError());
+      CUDA_TRY(cudaStreamSynchronize(p.stream));
+    }
+    CUDA_TRY(cudaMemcpy(p.h_dmid.data(), p.d_dmid.p, (size_t)tot * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> seg_dmid(K);
+    for (int k = 0; k < K; ++k)
+      seg_dmid[k] = p.dmid_off[std::lower_bound(p.degs.begin(), p.degs.end(), p.po[k]) - p.degs.begin()];
+    CUDA_TRY(up(p.d_seg_dmid, seg_dmid.data(), K * sizeof(int32_t)));
+    {
+      std::vector<int64_t> rpre;
+      for (auto& L : p.ph) rpre.insert(rpre.end(), L.seg_rpre.begin(), L.seg_rpre.end());
+      CUDA_TRY(up(p.d_seg_rpre, rpre.data(), rpre.size() * sizeof(int64_t)));
+    }
+    CUDA_TRY(p.d_wpart.ensure((size_t)K * sizeof(double)));
+    int njf = 0;
+    for (auto& L : p.ph) {
+      int n = 0;
+      for (uint8_t b : L.pat_f) n += b;
+      njf = std::max(njf, n);
+    }
+    const int n1 = dmax + 1;  // same formula as mpx_adapt_smem_doubles
+    p.smem_adapt = 8 * (MpxTab::pad2(n1) + 2 * MpxTab::pad2(dmax * n1) + MpxTab::pad2((nx + nu) * n1) +
+                        MpxTab::pad2(dmax * (3 * nx + njf + 2)));
+    if (p.smem_adapt > 227 * 1024) return fail(MPX_ELIMIT, "polynomial degree too large for the adaptive NLP kernel");
+  }
   build_structure(p);
   if (!p.gather.empty()) CUDA_TRY(up(p.d_gather, p.gather.data(), p.gather.size() * sizeof(int64_t)));
 
   // ---- work buffers
   CUDA_TRY(p.d_z.ensure((size_t)p.n_z * sizeof(double)));
   CUDA_TRY(p.d_p.ensure((size_t)p.n_p * sizeof(double)));
-  CUDA_TRY(p.d_sig0.ensure((size_t)p.n_p * sizeof(double)));
+  CUDA_TRY(p.d_sig0.ensure((size_t)K * p.P * sizeof(double)));
   CUDA_TRY(p.d_g.ensure((size_t)p.n_g * sizeof(double)));
   CUDA_TRY(p.d_vals.ensure((size_t)p.nnz * sizeof(double)));
   if (!p.gather.empty()) CUDA_TRY(p.d_full.ensure((size_t)p.nnz_full * sizeof(double)));
@@ -1187,7 +1364,17 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     for (int m = 0; m < na; ++m) a.isa[m] = 1.0 / p.sa[m];
     a.st = p.st, a.delta = p.tau_max - p.tau_min, a.tau0 = p.tau_min;
     a.ist = 1.0 / a.st, a.idelta = 1.0 / a.delta;
+    if (p.adaptive) {
+      a.ad_sw_u = L.sw_u, a.ad_sw_x = L.sw_x, a.ad_res = p.mid_res;
+      a.dmid = p.d_dmid.as<double>(), a.seg_dmid = p.d_seg_dmid.as<int32_t>();
+      a.seg_rpre = p.d_seg_rpre.as<int64_t>() + (int64_t)ph * K;
+      for (int s = 0; s < nx; ++s) a.eF[s] = L.eF[s];
+      for (int c = 0; c < L.nc; ++c) a.eC[c] = L.eC[c];
+      a.eSum = L.eSum, a.eUi = L.eUi, a.eXi = L.eXi, a.eRes = L.eRes, a.gSW = L.gSW;
+      a.wpart = p.d_wpart.as<double>();
+    }
   }
+  if (p.adaptive) p.origin += ";adaptive";
   *out = pp.release();
   return MPX_OK;
 }
@@ -1302,19 +1489,28 @@ extern "C" int mpx_shard_runs(const mpx_plan* p, int32_t kind, int64_t* runs, in
 }
 
 // ------------------------------------------------------------------ evaluation
+// segment widths of a phase: the NLP parameters p, or (adaptive NLP) decision variables at the end of the phase's z
+static const double* widths_of(const mpx_plan& p, const double* d_z, const double* d_p, int ph) {
+  return p.adaptive ? d_z + p.ph[ph].zoff + (p.nvar - p.K) : d_p + (int64_t)ph * p.K;
+}
+static void scan_widths(mpx_plan& p, const double* d_z, const double* d_p, cudaStream_t st) {
+  if (p.adaptive)
+    mpx_scan_widths_kernel<<<p.P, MPX_SCAN_THREADS, 0, st>>>(d_z + (p.nvar - p.K), p.d_sig0.as<double>(), p.K, p.nvar);
+  else
+    mpx_scan_widths_kernel<<<p.P, MPX_SCAN_THREADS, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K, p.K);
+  ++p.launches;
+}
+
 static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, double* d_g, double* d_vals, cudaStream_t st) {
   const bool jac = d_vals != nullptr;
   double* target = jac ? (p.gather.empty() ? d_vals : p.d_full.as<double>()) : nullptr;
   const int grid = p.seg_end - p.seg_begin;
   bool need_sig = false;
   for (auto& L : p.ph) need_sig |= L.uses_t;
-  if (need_sig) {
-    mpx_scan_widths_kernel<<<p.P, MPX_SCAN_THREADS, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
-    ++p.launches;
-  }
+  if (need_sig) scan_widths(p, d_z, d_p, st);
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs& a = p.args[ph];
-    a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
+    a.z = d_z, a.w = widths_of(p, d_z, d_p, ph), a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
     a.g = d_g, a.vals = target;
     if (p.v4) {
       a.stage_cap = p.v4_stage[ph], a.v4_nbuf = p.v4_nbuf[ph];
@@ -1335,6 +1531,11 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
       CUDA_TRY(p.prog->phases[ph]->gjac(a, jac, grid, jac ? p.smem_gjac : p.smem_g, st));
     ++p.launches;
     const PhaseLayout& L = p.ph[ph];
+    if (p.adaptive) {  // SW rows and the d/dw entries, staged behind the base kernels' values
+      a.ad_jac = jac ? 1 : 0, a.ext = jac ? p.d_full.as<double>() + p.n_base : nullptr;
+      CUDA_TRY(p.prog->phases[ph]->adapt(a, p.K, (size_t)p.smem_adapt, st));
+      ++p.launches;
+    }
     if (L.has_dU) {
       const int kb = p.seg_begin, ke = std::min(p.seg_end, p.K - 1);
       if (ke > kb) {
@@ -1369,13 +1570,10 @@ static int launch_f_grad(mpx_plan& p, const double* d_z, const double* d_p, doub
   const int grid = p.seg_end - p.seg_begin;
   bool need_sig = false;
   for (auto& L : p.ph) need_sig |= L.cost_t;
-  if (need_sig) {
-    mpx_scan_widths_kernel<<<p.P, MPX_SCAN_THREADS, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
-    ++p.launches;
-  }
+  if (need_sig) scan_widths(p, d_z, d_p, st);
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs& a = p.args[ph];
-    a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
+    a.z = d_z, a.w = widths_of(p, d_z, d_p, ph), a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
     a.node_begin = p.seg_begin == 0 ? 0 : p.seg_start[p.seg_begin] + 1, a.node_end = p.seg_start[p.seg_end] + 1;
     a.f_blocks = (a.node_end - a.node_begin + MPX_THREADS - 1) / MPX_THREADS;
     a.node_seg = p.d_node_seg.as<int32_t>();
@@ -1384,6 +1582,10 @@ static int launch_f_grad(mpx_plan& p, const double* d_z, const double* d_p, doub
     CUDA_TRY(p.prog->phases[ph]->fgrad(a, grad, a.f_blocks, 0, st));
     CUDA_TRY(p.prog->phases[ph]->fgrad_final(a, grad, st));
     p.launches += 2;
+    if (p.adaptive && grad) {  // d f / d w (mpopt.py:2945: the widths are part of x)
+      CUDA_TRY(p.prog->phases[ph]->adapt_grad(a, (p.K + MPX_THREADS - 1) / MPX_THREADS, st));
+      p.launches += 2;
+    }
   }
   return MPX_OK;
 }
@@ -1412,7 +1614,7 @@ static int download(mpx_plan& p, int kind, double* dst, const double* src, size_
 }
 
 static int upload_inputs(mpx_plan& p, const double* z, const double* pw) {
-  if (!z || !pw) return fail(MPX_EINVAL, "z and p must not be NULL");
+  if (!z || (!pw && p.n_p)) return fail(MPX_EINVAL, "z and p must not be NULL");
   CUDA_TRY(cudaSetDevice(p.device));
   if (p.seg_begin == 0 && p.seg_end == p.K) {
     CUDA_TRY(cudaMemcpyAsync(p.d_z.p, z, (size_t)p.n_z * sizeof(double), cudaMemcpyHostToDevice, p.stream));
@@ -1432,7 +1634,7 @@ static int upload_inputs(mpx_plan& p, const double* z, const double* pw) {
           CUDA_TRY(cudaMemcpyAsync(dz + off + v * p.N, z + off + v * p.N, sizeof(double), cudaMemcpyHostToDevice, p.stream));
     }
   }
-  if (!p.p_valid || memcmp(p.h_p_cache.data(), pw, (size_t)p.n_p * sizeof(double)) != 0) {
+  if (p.n_p && (!p.p_valid || memcmp(p.h_p_cache.data(), pw, (size_t)p.n_p * sizeof(double)) != 0)) {
     p.h_p_cache.assign(pw, pw + p.n_p);
     CUDA_TRY(cudaMemcpyAsync(p.d_p.p, p.h_p_cache.data(), (size_t)p.n_p * sizeof(double), cudaMemcpyHostToDevice, p.stream));
     p.p_valid = true;
@@ -1495,6 +1697,7 @@ struct HessEntry { int a, b, cat, slot; };
 int build_hessian(mpx_plan& p) {
   if (p.hess_built) return MPX_OK;
   if (p.seg_begin != 0 || p.seg_end != p.K) return fail(MPX_EINVAL, "the Hessian needs a plan over all segments");
+  if (p.adaptive) return fail(MPX_EINVAL, "the Hessian of the adaptive NLP (widths as variables) is not implemented");
   for (auto& L : p.ph)
     if (!L.has_hess) return fail(MPX_ENOPROGRAM, "the problem description carries no Hessian patterns (pat_hw / pat_ht)");
   const int nx = p.nx, nu = p.nu, na = p.na, ny = nx + nu, nv = ny + na, N = p.N, NW = nv + 2, NT = 2 * nx + 2 + na;
@@ -1655,8 +1858,7 @@ int build_hessian(mpx_plan& p) {
 
 int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f, const double* d_lam, double* d_vals,
                 cudaStream_t st) {
-  mpx_scan_widths_kernel<<<p.P, MPX_SCAN_THREADS, 0, st>>>(d_p, p.d_sig0.as<double>(), p.K);
-  ++p.launches;
+  scan_widths(p, d_z, d_p, st);
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs a = p.args[ph];
     auto& H = p.hess_ph[ph];
@@ -1729,10 +1931,9 @@ extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw
   CUDA_TRY(dout.ensure((size_t)n_points * per * sizeof(double)));
   CUDA_TRY(cudaMemcpyAsync(dseg.p, seg, (size_t)n_points * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream));
   CUDA_TRY(cudaMemcpyAsync(dtau.p, taus, (size_t)n_points * sizeof(double), cudaMemcpyHostToDevice, p->stream));
-  mpx_scan_widths_kernel<<<p->P, MPX_SCAN_THREADS, 0, p->stream>>>(p->d_p.as<double>(), p->d_sig0.as<double>(), p->K);
-  ++p->launches;
+  scan_widths(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->stream);
   MpxPhaseArgs a = p->args[phase];
-  a.z = p->d_z.as<double>(), a.w = p->d_p.as<double>() + (int64_t)phase * p->K;
+  a.z = p->d_z.as<double>(), a.w = widths_of(*p, p->d_z.as<double>(), p->d_p.as<double>(), phase);
   a.sig0 = p->d_sig0.as<double>() + (int64_t)phase * p->K;
   a.pt_seg = dseg.as<int32_t>(), a.pt_tau = dtau.as<double>(), a.n_points = n_points;
   double* o = dout.as<double>();
@@ -1816,7 +2017,7 @@ extern "C" int mpx_fetch(mpx_plan* p, int32_t what, double* out) {
 
 extern "C" int mpx_eval_g_jac_dev(mpx_plan* p, const double* d_z, const double* d_p, double* d_g, double* d_values,
                                   void* stream) {
-  if (!p || !d_z || !d_p || !d_g) return fail(MPX_EINVAL, "NULL argument");
+  if (!p || !d_z || (!d_p && p->n_p) || !d_g) return fail(MPX_EINVAL, "NULL argument");
   return launch_g_jac(*p, d_z, d_p, d_g, d_values, stream ? (cudaStream_t)stream : p->stream);
 }
 
@@ -1856,6 +2057,7 @@ extern "C" int mpx_peer_free(void* dptr) {
 extern "C" int mpx_eval_g_jac_dev_peers(mpx_plan* p, const double* d_z, const double* d_p, double* d_g, double* d_values,
                                         int32_t n_peers, double* const* peer_g, double* const* peer_values, void* stream) {
   if (!p || !d_z || !d_p || !d_g || !d_values) return fail(MPX_EINVAL, "NULL device pointer");
+  if (p->adaptive) return fail(MPX_EINVAL, "peer replication is not available for the adaptive NLP");
   if (n_peers < 0 || n_peers > MPX_MAX_PEERS || (n_peers && (!peer_g || !peer_values)))
     return fail(MPX_EINVAL, "n_peers must be in [0, 7] with both pointer arrays given");
   if (p->v4 || p->v2_warps == 0 || !p->gather.empty())
@@ -1910,7 +2112,7 @@ extern "C" int mpx_eval_g_jac_dev_peers(mpx_plan* p, const double* d_z, const do
 
 extern "C" int mpx_eval_f_grad_dev(mpx_plan* p, const double* d_z, const double* d_p, double* d_f, double* d_grad,
                                    void* stream) {
-  if (!p || !d_z || !d_p || !d_f) return fail(MPX_EINVAL, "NULL argument");
+  if (!p || !d_z || (!d_p && p->n_p) || !d_f) return fail(MPX_EINVAL, "NULL argument");
   return launch_f_grad(*p, d_z, d_p, d_f, d_grad, stream ? (cudaStream_t)stream : p->stream);
 }
 

@@ -23,6 +23,9 @@ struct MpxPhaseKernels {
   virtual cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const = 0;
   virtual cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const = 0;
   virtual cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const = 0;  // node kernel + final
+  // widths-as-variables NLP (mpopt_adaptive): extra rows / columns, and d f / d w
+  virtual cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const = 0;
+  virtual cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, cudaStream_t st) const = 0;
 };
 
 struct MpxProgramEntry {
@@ -147,6 +150,18 @@ struct MpxAotPhase final : MpxPhaseKernels {
   cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
     mpx_hess_kernel<PH><<<grid, MPX_HESS_THREADS, 0, st>>>(a);
     mpx_hess_final<PH><<<1, MPX_HESS_FINAL_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
+    static bool done = false;
+    cudaError_t e = allow_smem(mpx_adapt_kernel<PH>, smem, done);
+    if (e != cudaSuccess) return e;
+    mpx_adapt_kernel<PH><<<grid, MPX_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
+    mpx_adapt_grad_kernel<PH><<<grid, MPX_THREADS, 0, st>>>(a);
+    mpx_adapt_grad_suffix<PH><<<1, 32, 0, st>>>(a);
     return cudaGetLastError();
   }
 };

@@ -15,16 +15,21 @@ class PhaseLayout:
 
 
 class Layout:
-    def __init__(self, program, poly_orders, has_DU, has_mU, has_dU, n_links=0):
-        """``program``: mpopt_b200.program.Program; ``has_*``: per-phase booleans."""
+    def __init__(self, program, poly_orders, has_DU, has_mU, has_dU, n_links=0, adaptive=None):
+        """``program``: mpopt_b200.program.Program; ``has_*``: per-phase booleans.
+
+        ``adaptive``: None, or ``dict(sw_u=[..], sw_x=[..], mid_residuals=bool)`` for the NLP of ``mpopt_adaptive``
+        (mpopt.py:2877-3375): K width variables appended to every phase of z, rows ``[F, C, DU, TC, SW]`` per phase
+        (the value offsets ``v*`` then refer to the entries of the base kernels only)."""
         self.po = [int(v) for v in poly_orders]
         self.K = K = len(self.po)
         self.nx, self.nu, self.na, self.P = program.nx, program.nu, program.na, program.n_phases
         nx, nu, na = self.nx, self.nu, self.na
         self.seg_start = np.concatenate([[0], np.cumsum(self.po)]).astype(np.int64)
         self.N = N = int(self.seg_start[-1]) + 1
-        self.nvar = N * (nx + nu) + 2 + na
-        self.n_z, self.n_p = self.nvar * self.P, K * self.P
+        self.adaptive = adaptive
+        self.nvar = N * (nx + nu) + 2 + na + (K if adaptive else 0)
+        self.n_z, self.n_p = self.nvar * self.P, (0 if adaptive else K * self.P)
         po = np.asarray(self.po, dtype=np.int64)
         dcost = po * (po + 1)
         dcost0 = dcost.copy()
@@ -51,6 +56,10 @@ class Layout:
             L.gmU = row; row += nu * (N - 1) if L.has_mU else 0
             L.gdU = row; row += nu * (K - 1) if L.has_dU else 0
             L.gTC = row; row += L.ntc
+            if adaptive:  # mpopt.py:3034-3136
+                L.gSW = row
+                row += 1 + (nu * (N - 1) if adaptive["sw_u"][ph] else 0) + (nx * (N - 1) if adaptive["sw_x"][ph] else 0)
+                row += nx * (N - 1) if adaptive["mid_residuals"] else 0
             L.vF, L.vC = [], []
             for s in range(nx):
                 L.vF.append(val); val += self.nnzD + N * L.f_next[s]
@@ -81,6 +90,10 @@ class Layout:
 
     def colA(self, ph, m):
         return self.colT0(ph) + 2 + m
+
+    def colW(self, ph, k):
+        """Width variable of segment k (adaptive NLP only, mpopt.py:2938-2945)."""
+        return self.colT0(ph) + 2 + self.na + k
 
     # ---- sharding
     def owned_nodes(self, kb, ke):

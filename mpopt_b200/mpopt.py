@@ -129,6 +129,13 @@ class mpopt:
     def get_segment_width_parameters(self, solution=None):
         return [1.0 / self.n_segments] * (self.n_segments * self._ocp.n_phases)  # :723
 
+    def _current_widths(self):
+        """Width fractions of the last solve (``_nlp_sw_params``), equal widths before the first one."""
+        sw = getattr(self, "_nlp_sw_params", None)
+        if sw is None or len(sw) == 0:
+            sw = [1.0 / self.n_segments] * (self.n_segments * self._ocp.n_phases)
+        return np.asarray(sw, dtype=float)
+
     # ------------------------------------------------------------------ solver
     def create_solver(self, solver: str = "ipopt", options={}):
         nlp_problem, self.nlp_bounds = self.create_nlp()
@@ -201,7 +208,7 @@ class mpopt:
             self.compute_numerical_approximation()
         if grid_type is None:
             grid_type = self.grid_type[phase]
-        sw = np.asarray(getattr(self, "_nlp_sw_params", self.get_segment_width_parameters()), dtype=float)
+        sw = self._current_widths()
         if grid_type == "fixed":
             n_nodes = max(sum(self.poly_orders) + 2, self._MAX_GRID_POINTS + 2)
             target = np.linspace(self.tau0, self.tau1, n_nodes)
@@ -222,10 +229,10 @@ class mpopt:
             target_nodes = self.get_residual_grid_taus(phase=phase, grid_type=grid_type)
         tr, o = self.transcription, self._ocp
         z = np.asarray(solution["x"], dtype=float).reshape(-1)
-        sw = np.asarray(getattr(self, "_nlp_sw_params", self.get_segment_width_parameters()), dtype=float)
+        sw = self._current_widths()
         r = tr.residuals(z, sw, phase, target_nodes)
         L = tr.layout
-        a = z[L.colT0(phase) + 2: (phase + 1) * L.nvar]
+        a = z[L.colT0(phase) + 2: L.colT0(phase) + 2 + o.na]
         t0, tf = z[L.colT0(phase)] / o.scale_t, z[L.colTF(phase)] / o.scale_t
         self._last_residuals = r
         return (r["xi"], r["ui"], r["ti"].reshape(-1, 1), a, r["dxi"], r["dui"], target_nodes, np.atleast_1d(t0),
@@ -284,8 +291,8 @@ class post_process:
         X = z[off:off + o.nx * N].reshape(o.nx, N).T
         U = z[off + o.nx * N:off + (o.nx + o.nu) * N].reshape(o.nu, N).T
         T0, TF = z[L.colT0(phase)] / o.scale_t, z[L.colTF(phase)] / o.scale_t
-        A = z[L.colT0(phase) + 2:off + L.nvar]
-        w = np.asarray(getattr(mpo, "_nlp_sw_params", mpo.get_segment_width_parameters()), float)[phase * tr.K:(phase + 1) * tr.K]
+        A = z[L.colT0(phase) + 2:L.colT0(phase) + 2 + o.na]
+        w = mpo._current_widths()[phase * tr.K:(phase + 1) * tr.K]
         delta = tr.tau1 - tr.tau0
         t = np.empty(N)
         t[0], acc = T0, T0
@@ -336,7 +343,7 @@ class post_process:
             taus = [self.get_interpolation_taus(n=self._INTERPOLATION_NODES_PER_SEG)[1:] for _ in tr.poly_orders]
             taus[0] = np.append(tr.tau0, taus[0])
         z = np.asarray(self.solution["x"], dtype=float).reshape(-1)
-        sw = np.asarray(getattr(mpo, "_nlp_sw_params", mpo.get_segment_width_parameters()), dtype=float)
+        sw = mpo._current_widths()
         xs, us, ts, As = [], [], [], []
         for phase in phases:
             r = tr.residuals(z, sw, phase, taus, derivatives=False)

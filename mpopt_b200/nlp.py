@@ -24,7 +24,12 @@ def _u8(a):
 
 class Transcription:
     def __init__(self, ocp, n_segments=1, poly_orders=9, scheme="LGR", tau_min=-1.0, tau_max=1.0, device=0,
-                 drop_exact_zeros=True, segments=None, program=None):
+                 drop_exact_zeros=True, segments=None, program=None, adaptive=False, mid_residuals=True,
+                 width_bounds=(1e-4, 1.0), tol_residual=1e-3):
+        """``adaptive``: transcribe the NLP of the reference's ``mpopt_adaptive`` (mpopt.py:2877-3375) instead -- the
+        segment widths become decision variables appended to every phase of z, ``n_p = 0``, rows per phase
+        ``[F, C, DU, TC, SW]``; ``mid_residuals``, ``width_bounds = (lbh, ubh)`` and ``tol_residual`` are that class's
+        ``mid_residuals`` flag, ``lbh / ubh`` and ``tol_residual`` (:2896-2923)."""
         if scheme not in _lib.SCHEMES:
             raise ValueError(f"scheme must be one of {sorted(_lib.SCHEMES)} (got {scheme!r})")
         self.ocp = copy.deepcopy(ocp)  # the reference snapshots the OCP too (mpopt.py:77)
@@ -39,6 +44,9 @@ class Transcription:
         self.N = sum(self.poly_orders) + 1  # mpopt.py:84
         self.program = program if program is not None else Program(o)
         self.device = int(device)
+        self.adaptive, self.mid_residuals = bool(adaptive), bool(adaptive) and bool(mid_residuals)
+        self.lbh, self.ubh = [float(width_bounds[0])] * self.P, [float(width_bounds[1])] * self.P
+        self.tol_residual = [float(tol_residual)] * self.P
 
         # ---- description handed over the C ABI (arrays kept alive on self)
         L = _lib.lib()
@@ -48,18 +56,25 @@ class Transcription:
         for ph, pp in enumerate(self.program.phases):
             mid = bool(o.midu[ph]) and bool((np.asarray(o.lbu[ph]) > -np.inf).any() or
                                             (np.asarray(o.ubu[ph]) < np.inf).any())  # mpopt.py:346, :363-365
-            self.has_mU.append(mid)
+            self.has_mU.append(mid and not self.adaptive)
+            finite = lambda lo, hi: bool((np.asarray(lo) > -np.inf).any() or (np.asarray(hi) < np.inf).any())
             arrs = [_u8(pp.pat_f()), _u8(pp.f_nz), _u8(pp.f_t()), _u8(pp.pat_c()), _u8(pp.c_t()), _u8(pp.pat_tc()),
                     _u8(pp.pat_hw()), _u8(pp.pat_ht())]
             self._keep += arrs
             d = phases[ph]
             d.n_path, d.n_term = pp.nc, pp.ntc
             d.pat_f, d.f_nz, d.f_t, d.pat_c, d.c_t, d.pat_tc, d.pat_hw, d.pat_ht = [_lib.ptr(a, _lib.c_u8p) for a in arrs]
-            d.diff_u, d.midu = int(bool(o.diff_u[ph])), int(mid)
-            d.du_continuity = int(bool(o.du_continuity[ph]))
+            d.diff_u, d.midu = int(bool(o.diff_u[ph])), int(mid and not self.adaptive)
+            d.du_continuity = int(bool(o.du_continuity[ph]) and not self.adaptive)
+            d.sw_u = int(self.adaptive and finite(o.lbu[ph], o.ubu[ph]))  # mpopt.py:3066-3068
+            d.sw_x = int(self.adaptive and finite(o.lbx[ph], o.ubx[ph]))  # mpopt.py:3075-3077
             d.cost_t = int(not pp.Lt.is_value(0.0))
+        self.sw_u, self.sw_x = [bool(phases[ph].sw_u) for ph in range(self.P)], [bool(phases[ph].sw_x) for ph in range(self.P)]
         self.layout = Layout(self.program, self.poly_orders, [bool(v) for v in o.diff_u], self.has_mU,
-                             [bool(v) for v in o.du_continuity], len(o.phase_links) if self.P > 1 else 0)
+                             [bool(v) and not self.adaptive for v in o.du_continuity],
+                             len(o.phase_links) if self.P > 1 else 0,
+                             adaptive=dict(sw_u=self.sw_u, sw_x=self.sw_x, mid_residuals=self.mid_residuals)
+                             if self.adaptive else None)
         po = np.asarray(self.poly_orders, dtype=np.int32)
         sx, su, sa = (np.ascontiguousarray(np.asarray(v, dtype=float)) for v in (o.scale_x, o.scale_u, o.scale_a))
         links = np.asarray(o.phase_links if self.P > 1 else [], dtype=np.int32).reshape(-1)
@@ -77,6 +92,7 @@ class Transcription:
         desc.program_source = self.program.cuda_source().encode()
         desc.device = self.device
         desc.seg_begin, desc.seg_end = (0, 0) if segments is None else (int(segments[0]), int(segments[1]))
+        desc.adaptive, desc.mid_residuals = int(self.adaptive), int(self.mid_residuals)
         self.segments = (0, self.K) if segments is None else (int(segments[0]), int(segments[1]))
         plan = C.c_void_p()
         _lib.check(L.mpx_plan_create(C.byref(desc), C.byref(plan)))
@@ -123,7 +139,7 @@ class Transcription:
     # ------------------------------------------------------------------ evaluators (host buffers)
     def _zp(self, z, p):
         z = np.ascontiguousarray(z, dtype=float)
-        p = self.seg_width_params() if p is None else np.ascontiguousarray(p, dtype=float)
+        p = self.seg_width_params() if (p is None or self.adaptive) else np.ascontiguousarray(p, dtype=float)
         if z.shape != (self.n_z,) or p.shape != (self.n_p,):
             raise ValueError(f"expected z of shape ({self.n_z},) and p of shape ({self.n_p},)")
         return z, p
@@ -239,8 +255,9 @@ class Transcription:
 
     # ------------------------------------------------------------------ bounds, parameters, initial guess
     def seg_width_params(self):
-        """Equal segment widths summing to 1 per phase (mpopt.py:710-723)."""
-        return np.full(self.K * self.P, 1.0 / self.K)
+        """Equal segment widths summing to 1 per phase (mpopt.py:710-723); empty for the adaptive NLP, whose widths
+        are decision variables (:3190-3191)."""
+        return np.zeros(0) if self.adaptive else np.full(self.K * self.P, 1.0 / self.K)
 
     def bounds(self):
         """(Zmin, Zmax, Gmin, Gmax) in the layout of z and g."""
@@ -257,19 +274,33 @@ class Transcription:
                     np.asarray(o.lba[ph], float) * o.scale_a]
             zhi += [xhi.reshape(-1), uhi, np.atleast_1d(o.ubt0[ph] * o.scale_t), np.atleast_1d(o.ubtf[ph] * o.scale_t),
                     np.asarray(o.uba[ph], float) * o.scale_a]
+            if self.adaptive:  # width variables (mpopt.py:2958, :2976)
+                zlo.append(np.full(K, self.lbh[ph]))
+                zhi.append(np.full(K, self.ubh[ph]))
             glo += [np.full(nx * N, float(o.LB_DYNAMICS)), np.full(pp.nc * N, float(o.LB_PATH_CONSTRAINTS))]
             ghi += [np.full(nx * N, float(o.UB_DYNAMICS)), np.full(pp.nc * N, float(o.UB_PATH_CONSTRAINTS))]
             if o.diff_u[ph]:
                 glo.append(np.full(nu * N, float(o.lbdu[ph])))
                 ghi.append(np.full(nu * N, float(o.ubdu[ph])))
-            if self.has_mU[ph]:
+            if self.has_mU[ph] and not self.adaptive:
                 glo.append(np.repeat(np.asarray(o.lbu[ph], float) * o.scale_u, N - 1))
                 ghi.append(np.repeat(np.asarray(o.ubu[ph], float) * o.scale_u, N - 1))
-            if o.du_continuity[ph] and K > 1:
+            if o.du_continuity[ph] and K > 1 and not self.adaptive:
                 glo.append(np.zeros(nu * (K - 1)))
                 ghi.append(np.zeros(nu * (K - 1)))
             glo.append(np.full(pp.ntc, float(o.LB_TERMINAL_CONSTRAINTS)))
             ghi.append(np.full(pp.ntc, float(o.UB_TERMINAL_CONSTRAINTS)))
+            if self.adaptive:  # SW block (mpopt.py:3037-3130)
+                glo.append(np.zeros(1)), ghi.append(np.zeros(1))
+                if self.sw_u[ph]:
+                    glo.append(np.repeat(np.asarray(o.lbu[ph], float) * o.scale_u, N - 1))
+                    ghi.append(np.repeat(np.asarray(o.ubu[ph], float) * o.scale_u, N - 1))
+                if self.sw_x[ph]:
+                    glo.append(np.repeat(np.asarray(o.lbx[ph], float) * o.scale_x, N - 1))
+                    ghi.append(np.repeat(np.asarray(o.ubx[ph], float) * o.scale_x, N - 1))
+                if self.mid_residuals:
+                    glo.append(np.full(nx * (N - 1), -self.tol_residual[ph]))
+                    ghi.append(np.full(nx * (N - 1), self.tol_residual[ph]))
         if self.P > 1:
             n = len(o.phase_links)
             # the reference indexes lbe/ube by link ordinal, not by phase id (mpopt.py:491-497)
@@ -295,4 +326,6 @@ class Transcription:
             X = x0[None, :] + ((xf - x0) / (tb - ta))[None, :] * (ts - ta)[:, None]
             U = u0[None, :] + ((uf - u0) / (tb - ta))[None, :] * (ts - ta)[:, None]
             parts += [X.T.reshape(-1), U.reshape(-1), [ta], [tb], np.asarray(o.a0[ph], float) * o.scale_a]
+            if self.adaptive:  # mpopt.py:3030
+                parts.append(np.full(self.K, 1.0 / self.K))
         return np.concatenate([np.asarray(a, float).reshape(-1) for a in parts])

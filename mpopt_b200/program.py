@@ -268,6 +268,7 @@ class PhaseProgram:
         L.append(self._switch("f_next", next_, 0))
         L.append(self._switch("f_tpos", tpos))
         L.append(self._switch("f_diag", diag))
+        L.append(self._switch("f_t", self.f_t(), 0))
         first = lambda rows, n: [next((e for e, r in enumerate(rows) if r == k), 0) for k in range(n)]
         count = lambda rows, n: [sum(1 for r in rows if r == k) for k in range(n)]
         L.append(self._switch("jf_first", first(jf_row, nx), 0))

@@ -67,6 +67,7 @@ class ScipyNlpSolver:
             # exact second derivatives from the Hessian kernel (CasADi's nlp_hess_l) unless the caller asks for a
             # quasi-Newton model with IPOPT's option name
             exact = self.options.get("ipopt.hessian_approximation", self.options.get("hessian_approximation", "exact")) == "exact"
+            exact = exact and not getattr(tr, "adaptive", False)  # no Hessian kernel for the widths-as-variables NLP yet
             if exact:
                 zero_lam = np.zeros(n_g)
 

@@ -49,7 +49,7 @@ def hess_l(ora, z, p=None, lam_f=1.0, lam_g=None):
         X, U, T0, TF, A = ora._unpack(ph, z)
         w = p[ph * K: (ph + 1) * K]
         delta = ora.tau1 - ora.tau0
-        _, _, sigma, _ = ora._time_grid(ph, T0, TF, p)
+        _, _, sigma, _ = ora._time_grid(ph, T0, TF, w)
         wn = w[ora.node_seg]
         ones = np.ones(N)
         # raw decision variables as second-order duals, one entry per node

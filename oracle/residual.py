@@ -68,7 +68,7 @@ def interpolate_phase(ora, z, p, phase, taus):
     """mpopt.py:1489-1542: (Xi, Ui, ti, DXi, DUi) at the per-segment local taus (rows = points, segment by segment)."""
     X, U, T0, TF, A = ora._unpack(phase, np.asarray(z, dtype=float))
     p = ora.seg_width_params() if p is None else np.asarray(p, dtype=float)
-    _, t, _, _ = ora._time_grid(phase, T0, TF, p)
+    _, t, _, _ = ora._time_grid(phase, T0, TF, ora._widths(phase, z, p)[0])
     CI = ora.tab.composite_interpolation(taus, 0)
     DI = ora.tab.composite_interpolation(taus, 1)
     ti = interpolated_time_grid(t, taus, ora.po, ora.tau0, ora.tau1)

@@ -1,0 +1,223 @@
+"""GPU parity of the widths-as-variables NLP (``mp.mpopt_adaptive``) against oracle/adaptive.py, and
+the reference's adaptive tests (tests/test_mpopt.py:431-483, :498-546) re-read against ``mpopt_b200.mp``: the
+h-adaptive outer loop re-solves one device plan with new width parameters, the adaptive class solves for the widths."""
+import numpy as np
+import pytest
+
+from helpers import assert_close
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # name, problem, K, poly_orders, scheme, mid_residuals
+    ("moon_3x3", "moon_lander", 3, 3, "LGR", True),          # tests/test_mpopt.py:258-259
+    ("moon_nores", "moon_lander", 3, 3, "LGR", False),       # tests/test_mpopt.py:474
+    ("hyper_5x15", "hyper_sensitive", 5, 15, "LGR", True),   # tests/test_mpopt.py:276-277
+    ("hyper_3x30", "hyper_sensitive", 3, 30, "LGR", True),   # examples/singlephase/hyper_sensitive.py:82
+    ("vdp_mixed", "van_der_pol", 6, [3, 7, 2, 5, 4, 6], "CGL", True),
+    ("schwartz", "two_phase_schwartz", 4, 6, "LGL", True),
+    ("syn63", "synthetic_6_3", 12, 15, "LGR", True),
+    ("robot", "robot_arm", 5, 4, "LGR", True),
+    ("sink_time_dependent", "kitchen_sink", 5, [3, 4, 6, 2, 5], "LGR", True),
+    ("sink_p1", "kitchen_sink", 3, 1, "LGL", True),
+]
+
+
+def _point(n, problem, seed=20261017):
+    rng = np.random.default_rng(seed)
+    z = rng.uniform(-1.0, 1.0, n.n_z)
+    if problem == "robot_arm":
+        z = np.abs(z) + 0.5
+    for ph in range(n.P):
+        z[n.colT0(ph)] = 0.3 + 0.25 * ph
+        z[n.colTF(ph)] = 2.0 + 1.5 * ph
+        for m in range(n.na):
+            z[n.colA(ph, m)] = rng.uniform(0.2, 1.2)
+        z[n.colW(ph, np.arange(n.K))] = rng.dirichlet(np.ones(n.K)) * 0.8 + 0.2 / n.K
+    return z
+
+
+@pytest.mark.parametrize("name,problem,K,po,scheme,mid", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("drop", [False, True], ids=["structural", "folded"])
+def test_adaptive_nlp_matches_oracle(libmpx, name, problem, K, po, scheme, mid, drop):
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle.adaptive import OracleAdaptiveNLP
+
+    ocp = REGISTRY[problem]()
+    tr = Transcription(ocp, K, po, scheme, adaptive=True, mid_residuals=mid, drop_exact_zeros=drop)
+    tabs = None
+    if drop:  # exact-zero folding is decided on the device's own tables (checked against the oracle's first)
+        plain = OracleAdaptiveNLP(ocp, K, po, scheme, drop_exact_zeros=False, mid_residuals=mid)
+        tabs = {}
+        for d in sorted(set(tr.poly_orders)):
+            r, D, w, Cm = tr.tables(d)
+            assert_close(D, plain.tab.D[d], f"D[{d}]", 1e-11)
+            assert_close(Cm, plain.tab.Cmid[d], f"Cmid[{d}]", 1e-12)
+            tabs[d] = (r, D, w, Cm)
+    ora = OracleAdaptiveNLP(ocp, K, po, scheme, drop_exact_zeros=drop, mid_residuals=mid, tables=tabs)
+    assert (tr.n_z, tr.n_p, tr.n_g) == (ora.n_z, 0, ora.n_g)
+    assert tr.program_origin.endswith(";adaptive")
+    z = _point(ora, problem)
+    J = ora.jac_g(z)
+    rp, ci = tr.structure()
+    assert np.array_equal(rp, J.indptr), "rowptr differs from the oracle"
+    assert np.array_equal(ci, J.indices), "colind differs from the oracle"
+    g = np.empty(tr.n_g)
+    vals = tr.jac_g_values(z, g_out=g)
+    assert_close(g, ora.g(z), "g")
+    assert_close(tr.g(z), ora.g(z), "g (g-only launch)")
+    assert_close(vals, J.data, "jac_g values")
+    assert abs(tr.f(z) - ora.f(z)) <= 1e-10 * max(1.0, abs(ora.f(z)))
+    assert_close(tr.grad_f(z), ora.grad_f(z), "grad_f")
+    for a, b in zip(tr.bounds(), ora.bounds()):
+        assert np.array_equal(a, b)
+    assert np.allclose(tr.initial_guess(), ora.initialize_solution(), rtol=0, atol=1e-15)
+    # a second point: nothing cached between evaluations
+    z2 = z + 1e-3 * np.random.default_rng(1).standard_normal(tr.n_z)
+    assert_close(tr.jac_g_values(z2), ora.jac_g(z2).data, "jac_g values, second point")
+
+
+def test_adaptive_nlp_runtime_compiled_program(libmpx):
+    """An unregistered problem goes through NVRTC: the adaptive kernels are part of the run-time module."""
+    from mpopt_b200 import ca
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.ocp import OCP
+    from oracle.adaptive import OracleAdaptiveNLP
+
+    ocp = OCP(n_states=2, n_controls=1)
+    ocp.dynamics[0] = lambda x, u, t: [x[1] * ca.cos(0.37 * t), u[0] - 0.21 * x[0] * x[1]]
+    ocp.running_costs[0] = lambda x, u, t: u[0] * u[0] + 0.13 * t * x[0]
+    ocp.lbu[0], ocp.ubu[0] = -1, 1
+    ocp.validate()
+    tr = Transcription(ocp, 4, [3, 5, 2, 4], "LGR", adaptive=True, drop_exact_zeros=False)
+    ora = OracleAdaptiveNLP(ocp, 4, [3, 5, 2, 4], "LGR", drop_exact_zeros=False)
+    assert tr.program_origin.startswith("nvrtc:")
+    z = _point(ora, "x")
+    J = ora.jac_g(z)
+    rp, ci = tr.structure()
+    assert np.array_equal(rp, J.indptr) and np.array_equal(ci, J.indices)
+    assert_close(tr.jac_g_values(z), J.data, "jac_g values")
+    assert_close(tr.g(z), ora.g(z), "g")
+    assert_close(tr.grad_f(z), ora.grad_f(z), "grad_f")
+
+
+def test_adaptive_plan_refuses_what_it_cannot_do(libmpx):
+    from mpopt_b200 import _lib
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import moon_lander
+
+    with pytest.raises(_lib.MpxError):
+        Transcription(moon_lander(), 4, 3, "LGR", adaptive=True, segments=(0, 2))
+    tr = Transcription(moon_lander(), 4, 3, "LGR", adaptive=True)
+    with pytest.raises(_lib.MpxError):
+        tr.hess_structure()
+
+
+# ---------------------------------------------------------------------------- the reference's adaptive tests
+@pytest.fixture(scope="module")
+def mp(libmpx):
+    from mpopt_b200 import mp as _mp
+
+    _mp.mpopt._MUTE_ = True
+    return _mp
+
+
+def _check_post(mpo, sol):
+    for key in ("x", "f"):
+        assert key in sol
+    post = mpo.process_results(sol, plot=False)
+    x, u, t, _ = post.get_data()
+    xi, ui, ti, _ = post.get_data(interpolate=True)
+    assert x.shape[0] == u.shape[0] == t.shape[0]
+    assert xi.shape[0] == ui.shape[0] == ti.shape[0]
+    return post
+
+
+@pytest.mark.parametrize("grid,max_iter,options", [
+    ("fixed", 3, {}),                                                            # tests/test_mpopt.py:431-440
+    ("mid-points", 2, {"method": "residual", "sub_method": "equal_area"}),      # :443-455
+    ("spectral", 10, {"method": "control_slope", "sub_method": ""}),            # :458-470
+    ("fixed", 3, {"method": "residual", "sub_method": "merge_split"}),
+])
+def test_moon_lander_h_adaptive_solve(mp, grid, max_iter, options):
+    from mpopt_b200.problems import moon_lander
+
+    mpo = mp.mpopt_h_adaptive(moon_lander(), 10, 4)
+    mpo.grid_type[0] = grid
+    plan = mpo.transcription
+    sol = mpo.solve(max_iter=max_iter, mpopt_options=dict(options))
+    assert mpo.transcription is plan, "the refinement loop must reuse the device plan (widths are parameters)"
+    assert 1 <= mpo.iter_count <= max_iter
+    sw = np.asarray(mpo._nlp_sw_params, float)
+    assert sw.shape == (10,) and abs(sw.sum() - 1) < 1e-9 and (sw > 0).all()
+    assert abs(sol["f"] - 8.2477) < 5e-2   # docs/source/notebooks/moon_lander.ipynb:185
+    _check_post(mpo, sol)
+
+
+def test_h_adaptive_reduces_the_residual(mp):
+    """The point of the loop: moving the segment boundaries towards the bang-bang switch lowers the max residual."""
+    from mpopt_b200.problems import moon_lander
+
+    mpo = mp.mpopt_h_adaptive(moon_lander(), 10, 4)
+    mpo.solve(max_iter=4, mpopt_options={"method": "residual", "sub_method": "merge_split"})
+    errs = [v for v in mpo.iter_info.values() if v is not None]
+    assert len(errs) >= 2 and errs[-1] < errs[0]
+
+
+def test_hyper_sensitive_h_adaptive_solve(mp):
+    """tests/test_mpopt.py:268-269, :498-507 at a size SciPy's solver handles in seconds."""
+    from mpopt_b200.problems import hyper_sensitive
+
+    mpo = mp.mpopt_h_adaptive(hyper_sensitive(), 6, 8)
+    sol = mpo.solve(max_iter=2, mpopt_options={"method": "residual", "sub_method": "merge_split"})
+    _check_post(mpo, sol)
+
+
+def test_h_adaptive_static_helpers(mp):
+    H = mp.mpopt_h_adaptive
+    # equal residual everywhere -> equal widths
+    w = H.get_roots_wrt_equal_area(np.ones(21), 4)
+    assert np.allclose(w, 0.25)
+    # two good segments merge, the bad one is split in two
+    w = H.merge_split_segments_based_on_residuals([1e-6, 1e-6, 1.0], [0.25, 0.25, 0.5], ERR_TOL=1e-3)
+    assert np.allclose(w, [0.5, 0.25, 0.25])
+    # nothing to merge: unchanged
+    w0 = [0.5, 0.5]
+    assert H.merge_split_segments_based_on_residuals([1.0, 1e-6], w0, ERR_TOL=1e-3) is w0
+    w = H.compute_segment_widths_at_times(np.array([1.0, 3.0]), 3, 0.0, 4.0)
+    assert np.allclose(w, [0.25, 0.5, 0.25])
+    w = H.compute_segment_widths_at_times(np.array([2.0]), 4, 0.0, 4.0)
+    assert abs(w.sum() - 1) < 1e-12 and len(w) == 4
+
+
+def test_moon_lander_mpopt_adaptive_solve(mp):
+    """tests/test_mpopt.py:258-259, :473-483."""
+    from mpopt_b200.problems import moon_lander
+
+    mpo = mp.mpopt_adaptive(moon_lander(), 3, 3)
+    mpo.mid_residuals = False
+    sol = mpo.solve()
+    post = _check_post(mpo, sol)
+    sw = mpo._nlp_sw_params
+    assert sw.shape == (3,) and abs(sw.sum() - 1) < 1e-6 and (sw >= 1e-4 - 1e-9).all()
+    zmin, zmax, gmin, gmax = mpo.transcription.bounds()
+    assert (sol["g"] >= gmin - 1e-5).all() and (sol["g"] <= gmax + 1e-5).all()
+    assert abs(sol["f"] - 8.2477) < 0.2
+    x, u, t, _ = post.get_data()
+    assert abs(x[0, 0] - 10.0) < 1e-9 and abs(x[-1, 0]) < 1e-5
+
+
+def test_hyper_sensitive_mpopt_adaptive_structure(mp):
+    """tests/test_mpopt.py:276-277: mpopt_adaptive(hyper_sensitive, 5, 15) -- sizes of the NLP the reference builds."""
+    from mpopt_b200.problems import hyper_sensitive
+
+    mpo = mp.mpopt_adaptive(hyper_sensitive(), 5, 15)
+    nlp, bounds = mpo.create_nlp()
+    N = 76
+    assert nlp["x"] == 2 * N + 2 + 5 and nlp["p"] == 0
+    # F N | TC 1 | sum 1 | residuals N-1   (no finite state / control bounds in this problem)
+    assert bounds["lbg"].shape[0] == N + 1 + 1 + (N - 1)
+    SW, SWmin, SWmax = mpo.get_nlp_constrains_for_segment_widths(0)
+    assert len(SW) == 1 + (N - 1) and SWmin[0] == SWmax[0] == 0 and (SWmax[1:] == 1e-3).all()
+    assert mpo.initialize_solution().shape[0] == nlp["x"]
