@@ -110,6 +110,10 @@ def build(force=False, verbose=False):
     with cf.ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
         results = list(ex.map(lambda s: _compile(s, force), srcs))
     objs = [o for o, _ in results]
+    keep = {os.path.basename(o) for o in objs}
+    for fn in os.listdir(OBJ):  # objects of programs that are no longer generated (their hash changed)
+        if fn.endswith((".o", ".o.sha")) and fn.replace(".sha", "") not in keep:
+            os.remove(os.path.join(OBJ, fn))
     rebuilt = [l for _, l in results if l is not None]
     if rebuilt:
         with open(os.path.join(OBJ, "ptxas.log"), "a" if len(rebuilt) < len(results) else "w") as f:

@@ -1167,7 +1167,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     }
     const int n1 = dmax + 1;  // same formula as mpx_adapt_smem_doubles
     p.smem_adapt = 8 * (MpxTab::pad2(n1) + 2 * MpxTab::pad2(dmax * n1) + MpxTab::pad2((nx + nu) * n1) +
-                        MpxTab::pad2(dmax * (3 * nx + njf + 2)));
+                        MpxTab::pad2(dmax * (3 * nx + njf + 2)) + MpxTab::pad2(dmax * (2 * nx + nu)));
     if (p.smem_adapt > 227 * 1024) return fail(MPX_ELIMIT, "polynomial degree too large for the adaptive NLP kernel");
   }
   build_structure(p);

@@ -269,6 +269,14 @@ class PhaseProgram:
         L.append(self._switch("f_tpos", tpos))
         L.append(self._switch("f_diag", diag))
         L.append(self._switch("f_t", self.f_t(), 0))
+        # (row s, node variable v) -> entry of jf or -1; column blocks / parameter entries of a mid-point residual row
+        # of the adaptive NLP (mpx_adapt_kernel)
+        nvv = nx + nu + na
+        jf_at = {(r, v): e for e, (r, v, _) in enumerate(self.jf)}
+        L.append(self._switch("jf_index", [jf_at.get((s, v), -1) for s in range(nx) for v in range(nvv)]))
+        L.append(self._switch("res_nblk", [sum(1 for v in range(nx + nu) if v == s or (s, v) in jf_at)
+                                           for s in range(nx)], 0))
+        L.append(self._switch("res_na", [sum(1 for m in range(na) if (s, nx + nu + m) in jf_at) for s in range(nx)], 0))
         first = lambda rows, n: [next((e for e, r in enumerate(rows) if r == k), 0) for k in range(n)]
         count = lambda rows, n: [sum(1 for r in rows if r == k) for k in range(n)]
         L.append(self._switch("jf_first", first(jf_row, nx), 0))
