@@ -218,7 +218,10 @@ struct mpx_plan {
   std::vector<int> dmid_off;               // per unique degree: record offset in h_dmid
   std::vector<double> h_dmid;              // D at the mid points, [d][d+1] per degree
   DevBuf d_dmid, d_seg_dmid, d_wpart, d_seg_rpre;  // d_seg_rpre: [P][K]
+  DevBuf d_ticket;                                 // [P] arrival counters of the single-launch f + grad_f kernel
   int smem_adapt = 0;
+  std::vector<int64_t> sw_direct;          // per phase: CSR position of the SW block when it is written in place, else -1
+  std::vector<int64_t> gather_runs;        // (first, count) CSR ranges that go through the gather (empty: everything)
   int64_t nvar, n_z, n_p, n_g, nnz_full, nnz;
   int64_t nnzD, nnzI, nnzS;
   int64_t g_events, v_events;
@@ -493,9 +496,9 @@ struct MpxRtPhase final : MpxPhaseKernels {
   cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
     return go(f_adapt[0], a, grid, MPX_THREADS, smem, st);
   }
-  cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
+  cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const override {
     cudaError_t e = go(f_adapt[1], a, grid, MPX_THREADS, 0, st);
-    return e != cudaSuccess ? e : go(f_adapt[2], a, 1, 32, 0, st);
+    return e != cudaSuccess || !suffix ? e : go(f_adapt[2], a, 1, 32, 0, st);
   }
 };
 
@@ -919,6 +922,27 @@ static void build_structure(mpx_plan& p) {
     }
   }
   p.nnz = (int64_t)p.colind.size();
+  // adaptive NLP: an SW block whose CSR entries are exactly its ext entries in order is written in place
+  p.sw_direct.assign(p.P, -1), p.gather_runs.clear();
+  if (p.adaptive) {
+    int64_t done = 0;  // CSR entries before this point are covered by gather runs or in-place blocks
+    for (int ph = 0; ph < p.P; ++ph) {
+      const PhaseLayout& L = p.ph[ph];
+      const int64_t rb = L.gSW, re = ph + 1 < p.P ? p.ph[ph + 1].gF : p.g_events;
+      const int64_t a = p.rowptr[rb], b = p.rowptr[re];
+      bool direct = b > a && p.gather[a] == p.n_base + L.eSum;
+      for (int64_t e = a + 1; e < b && direct; ++e) direct = p.gather[e] == p.gather[e - 1] + 1;
+      if (direct) {
+        p.sw_direct[ph] = a;
+        if (a > done) p.gather_runs.push_back(done), p.gather_runs.push_back(a - done);
+        done = b;
+      }
+    }
+    if (p.nnz > done) p.gather_runs.push_back(done), p.gather_runs.push_back(p.nnz - done);
+    bool any = false;
+    for (int64_t v : p.sw_direct) any |= v >= 0;
+    if (!any) p.gather_runs.clear();
+  }
 }
 
 // ------------------------------------------------------------------ plan creation
@@ -1189,6 +1213,13 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     CUDA_TRY(up(p.d_node_seg, node_seg.data(), node_seg.size() * sizeof(int32_t)));
   }
   CUDA_TRY(p.d_f.ensure(sizeof(double)));
+  {
+    const char* fe = getenv("MPX_FGRAD_FUSED");  // 0: node kernel + separate final sum (two launches), for measurements
+    if (!fe || atoi(fe)) {
+      CUDA_TRY(p.d_ticket.ensure((size_t)p.P * sizeof(unsigned int)));
+      CUDA_TRY(cudaMemset(p.d_ticket.p, 0, (size_t)p.P * sizeof(unsigned int)));
+    }
+  }
 
   // ---- shared-memory budget (same formulas as the kernels)
   {
@@ -1533,6 +1564,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     const PhaseLayout& L = p.ph[ph];
     if (p.adaptive) {  // SW rows and the d/dw entries, staged behind the base kernels' values
       a.ad_jac = jac ? 1 : 0, a.ext = jac ? p.d_full.as<double>() + p.n_base : nullptr;
+      a.ext_sw = !jac ? nullptr : (p.sw_direct[ph] >= 0 ? d_vals + p.sw_direct[ph] - L.eSum : a.ext);
       CUDA_TRY(p.prog->phases[ph]->adapt(a, p.K, (size_t)p.smem_adapt, st));
       ++p.launches;
     }
@@ -1556,9 +1588,16 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     CUDA_TRY(cudaGetLastError());
     ++p.launches;
   }
-  if (jac && !p.gather.empty()) {
+  if (jac && !p.gather.empty() && p.gather_runs.empty()) {
     mpx_compact_kernel<<<(unsigned)((p.nnz + 255) / 256), 256, 0, st>>>(p.d_full.as<double>(), p.d_gather.as<int64_t>(),
                                                                        d_vals, p.nnz);
+    CUDA_TRY(cudaGetLastError());
+    ++p.launches;
+  }
+  for (size_t i = 0; jac && i + 1 < p.gather_runs.size(); i += 2) {  // adaptive NLP: everything but the in-place SW blocks
+    const int64_t off = p.gather_runs[i], n = p.gather_runs[i + 1];
+    mpx_compact_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.d_full.as<double>(), p.d_gather.as<int64_t>() + off,
+                                                                   d_vals + off, n);
     CUDA_TRY(cudaGetLastError());
     ++p.launches;
   }
@@ -1579,12 +1618,16 @@ static int launch_f_grad(mpx_plan& p, const double* d_z, const double* d_p, doub
     a.node_seg = p.d_node_seg.as<int32_t>();
     a.grad = d_grad, a.partial = p.d_partial.as<double>() + (int64_t)ph * ((p.N + MPX_THREADS - 1) / MPX_THREADS + 1) * MPX_NPART;
     a.fout = d_f;
+    a.ticket = p.d_ticket.p ? p.d_ticket.as<unsigned int>() + ph : nullptr;
     CUDA_TRY(p.prog->phases[ph]->fgrad(a, grad, a.f_blocks, 0, st));
-    CUDA_TRY(p.prog->phases[ph]->fgrad_final(a, grad, st));
-    p.launches += 2;
+    ++p.launches;
+    if (!a.ticket) {  // otherwise the last CTA of the node kernel has done the final sum
+      CUDA_TRY(p.prog->phases[ph]->fgrad_final(a, grad, st));
+      ++p.launches;
+    }
     if (p.adaptive && grad) {  // d f / d w (mpopt.py:2945: the widths are part of x)
-      CUDA_TRY(p.prog->phases[ph]->adapt_grad(a, (p.K + MPX_THREADS - 1) / MPX_THREADS, st));
-      p.launches += 2;
+      CUDA_TRY(p.prog->phases[ph]->adapt_grad(a, (p.K + MPX_THREADS - 1) / MPX_THREADS, p.ph[ph].cost_t, st));
+      p.launches += p.ph[ph].cost_t ? 2 : 1;
     }
   }
   return MPX_OK;

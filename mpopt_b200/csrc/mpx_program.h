@@ -25,7 +25,7 @@ struct MpxPhaseKernels {
   virtual cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const = 0;  // node kernel + final
   // widths-as-variables NLP (mpopt_adaptive): extra rows / columns, and d f / d w
   virtual cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const = 0;
-  virtual cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, cudaStream_t st) const = 0;
+  virtual cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const = 0;
 };
 
 struct MpxProgramEntry {
@@ -159,9 +159,9 @@ struct MpxAotPhase final : MpxPhaseKernels {
     mpx_adapt_kernel<PH><<<grid, MPX_THREADS, smem, st>>>(a);
     return cudaGetLastError();
   }
-  cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
+  cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const override {
     mpx_adapt_grad_kernel<PH><<<grid, MPX_THREADS, 0, st>>>(a);
-    mpx_adapt_grad_suffix<PH><<<1, 32, 0, st>>>(a);
+    if (suffix) mpx_adapt_grad_suffix<PH><<<1, 32, 0, st>>>(a);  // time-dependent running cost only
     return cudaGetLastError();
   }
 };

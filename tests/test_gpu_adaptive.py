@@ -221,3 +221,24 @@ def test_hyper_sensitive_mpopt_adaptive_structure(mp):
     SW, SWmin, SWmax = mpo.get_nlp_constrains_for_segment_widths(0)
     assert len(SW) == 1 + (N - 1) and SWmin[0] == SWmax[0] == 0 and (SWmax[1:] == 1e-3).all()
     assert mpo.initialize_solution().shape[0] == nlp["x"]
+
+
+def test_h_adaptive_width_update_two_phases(mp):
+    """Width update of a two-phase problem from a given point (no solve): per-phase widths stay normalised, the
+    residuals come from the GPU kernel, every method returns one width per segment and phase (mpopt.py:2474-2592)."""
+    from mpopt_b200.problems import two_phase_schwartz
+
+    mpo = mp.mpopt_h_adaptive(two_phase_schwartz(), 5, 4)
+    mpo.create_solver()
+    rng = np.random.default_rng(3)
+    z = mpo.initialize_solution() + 0.05 * rng.standard_normal(mpo.transcription.n_z)
+    sol = {"x": z}
+    for options in ({"method": "residual", "sub_method": "equal_area"}, {"method": "residual", "sub_method": "merge_split"},
+                    {"method": "control_slope"}):
+        w, err = mpo.get_segment_width_parameters(sol, options=options)
+        w = np.asarray(w, float)
+        assert w.shape == (10,) and err is not None and err > 0
+        assert abs(w[:5].sum() - 1) < 1e-9 and abs(w[5:].sum() - 1) < 1e-9 and (w > 0).all()
+    ti, res = mpo.get_dynamics_residuals(sol)
+    assert len(res) == 2 and len(res[0]) == 5
+    assert abs(max(np.abs(r).max() for ph in res for r in ph if r is not None) - err) < 1e-12
