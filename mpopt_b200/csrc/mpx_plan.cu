@@ -491,7 +491,7 @@ struct MpxRtPhase final : MpxPhaseKernels {
   }
   cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
     cudaError_t e = go(f_hess[0], a, grid, MPX_HESS_THREADS, 0, st);
-    return e != cudaSuccess ? e : go(f_hess[1], a, 1, MPX_HESS_FINAL_THREADS, 0, st);
+    return e != cudaSuccess || a.ticket ? e : go(f_hess[1], a, 1, MPX_HESS_FINAL_THREADS, 0, st);
   }
   cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
     return go(f_adapt[0], a, grid, MPX_THREADS, smem, st);
@@ -1201,6 +1201,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   CUDA_TRY(p.d_z.ensure((size_t)p.n_z * sizeof(double)));
   CUDA_TRY(p.d_p.ensure((size_t)p.n_p * sizeof(double)));
   CUDA_TRY(p.d_sig0.ensure((size_t)K * p.P * sizeof(double)));
+  CUDA_TRY(cudaMemset(p.d_sig0.p, 0, (size_t)K * p.P * sizeof(double)));  // read (times 0) even when nothing depends on t
   CUDA_TRY(p.d_g.ensure((size_t)p.n_g * sizeof(double)));
   CUDA_TRY(p.d_vals.ensure((size_t)p.nnz * sizeof(double)));
   if (!p.gather.empty()) CUDA_TRY(p.d_full.ensure((size_t)p.nnz_full * sizeof(double)));
@@ -1216,8 +1217,8 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   {
     const char* fe = getenv("MPX_FGRAD_FUSED");  // 0: node kernel + separate final sum (two launches), for measurements
     if (!fe || atoi(fe)) {
-      CUDA_TRY(p.d_ticket.ensure((size_t)p.P * sizeof(unsigned int)));
-      CUDA_TRY(cudaMemset(p.d_ticket.p, 0, (size_t)p.P * sizeof(unsigned int)));
+      CUDA_TRY(p.d_ticket.ensure((size_t)2 * p.P * sizeof(unsigned int)));  // [P] f + grad_f, [P] hess_l
+      CUDA_TRY(cudaMemset(p.d_ticket.p, 0, (size_t)2 * p.P * sizeof(unsigned int)));
     }
   }
 
@@ -1901,10 +1902,13 @@ int build_hessian(mpx_plan& p) {
 
 int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f, const double* d_lam, double* d_vals,
                 cudaStream_t st) {
-  scan_widths(p, d_z, d_p, st);
+  bool need_sig = false;  // sigma only enters through explicit time dependence
+  for (auto& L : p.ph) need_sig |= L.uses_t || L.cost_t;
+  if (need_sig) scan_widths(p, d_z, d_p, st);
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs a = p.args[ph];
     auto& H = p.hess_ph[ph];
+    a.ticket = p.d_ticket.p ? p.d_ticket.as<unsigned int>() + p.P + ph : nullptr;
     a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
     a.lam = d_lam, a.lam_f = lam_f, a.node_seg = p.d_node_seg.as<int32_t>();
     a.hp_yy = H.pos_yy.as<int64_t>(), a.hp_ay = H.pos_ay.as<int64_t>(), a.hp_ty = H.pos_ty.as<int64_t>();
@@ -1913,7 +1917,7 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
     a.hp_term_assign = H.term_assign.as<int32_t>();
     a.hvals = d_vals, a.hpart = H.part.as<double>(), a.h_blocks = H.blocks;
     CUDA_TRY(p.prog->phases[ph]->hess(a, H.blocks, st));
-    p.launches += 2;
+    p.launches += a.ticket ? 1 : 2;
   }
   return MPX_OK;
 }

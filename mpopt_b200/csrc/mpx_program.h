@@ -149,7 +149,7 @@ struct MpxAotPhase final : MpxPhaseKernels {
   }
   cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
     mpx_hess_kernel<PH><<<grid, MPX_HESS_THREADS, 0, st>>>(a);
-    mpx_hess_final<PH><<<1, MPX_HESS_FINAL_THREADS, 0, st>>>(a);
+    if (!a.ticket) mpx_hess_final<PH><<<1, MPX_HESS_FINAL_THREADS, 0, st>>>(a);  // else done by the node kernel's last CTA
     return cudaGetLastError();
   }
   cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
