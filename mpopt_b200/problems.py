@@ -193,6 +193,118 @@ def kitchen_sink():
     return ocp
 
 
+def delta3_launch_vehicle(drag=0.0):
+    """Four-phase ascent of the Delta III to a geostationary transfer orbit: 7 states (position, velocity, mass in an
+    Earth-centred inertial frame), 3 controls (thrust direction), path rows |u| = 1 and r >= Re, orbital-element
+    terminal constraints, mass jumps at the stage separations, heavy scaling.
+
+    Restates the OCP of the reference's examples/Multi-phase/multistage_launch_vehicle.py:35-296 (the problem behind
+    docs/source/notebooks/multi_stage_launch_vehicle_ascent.ipynb, whose IPOPT banner -- 474 variables, 374 equalities,
+    276 inequalities at one segment of degree 11 per phase, :466-471 -- pins the layout of a 4-phase NLP with events).
+    ``drag`` is the example's ``param``: 0 switches the aerodynamic term off, and the 0 * D products then fold out of
+    the Jacobian pattern as they do in CasADi."""
+    Re, omega, mu = 6378145.0, 7.29211585e-5, 3.986012e14
+    rho0, scale_h, area_cd = 1.225, 7200.0, 4 * np.pi * 0.5
+    lat = 28.5 * np.pi / 180.0
+    r_pad = np.array([Re * np.cos(lat), 0.0, Re * np.sin(lat)])
+    v_pad = omega * np.array([-r_pad[1], r_pad[0], 0.0])
+    m_lift, m_payload = 301454.0, 4164.0
+    srb_prop, srb_dry = 17010.0, 19290.0 - 17010.0
+    first_prop, first_dry = 95550.0, 104380.0 - 95550.0
+    second_prop, second_dry = 16820.0, 19300.0 - 16820.0
+    srb_burn, first_burn, second_burn = 75.2, 261.0, 700.0
+    thrust = [6 * 628500.0 + 1083100.0, 3 * 628500.0 + 1083100.0, 1083100.0, 110094.0]
+    flow = [6 * srb_prop / srb_burn + first_prop / first_burn, 3 * srb_prop / srb_burn + first_prop / first_burn,
+            first_prop / first_burn, second_prop / second_burn]
+
+    def norm3(v):
+        return ca.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+
+    def make_dynamics(T, mdot):
+        def f(x, u, t):
+            r, v, m = x[:3], x[3:6], x[6]
+            rm = norm3(r)
+            vrel = ca.vertcat(v[0] + r[1] * omega, v[1] - r[0] * omega, v[2])
+            rho = rho0 * ca.exp(-(rm - Re) / scale_h)
+            D = -rho / (2 * m) * area_cd * norm3(vrel) * vrel
+            grav = -mu / (rm * rm * rm) * r
+            return [x[3], x[4], x[5]] + [T / m * u[i] + drag * D[i] + grav[i] for i in range(3)] + [-mdot]
+        return f
+
+    def path(x, u, t):
+        uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2]
+        return [uu - 1, -uu + 1, -norm3(x) / Re + 1]
+
+    a_req, e_req, i_req = 24361140.0, 0.7308, 28.5 * np.pi / 180.0
+    node_req, argp_req = 269.8 * np.pi / 180.0, 130.5 * np.pi / 180.0
+
+    def orbit(x, t, x0, t0):
+        """Orbital elements of the final state minus the targets."""
+        h = ca.vertcat(x[1] * x[5] - x[4] * x[2], x[3] * x[2] - x[0] * x[5], x[0] * x[4] - x[1] * x[3])
+        n = ca.vertcat(-h[1], h[0], 0)
+        r = norm3(x)
+        e = ca.vertcat(1 / mu * (x[4] * h[2] - x[5] * h[1]) - x[0] / r,
+                       1 / mu * (x[5] * h[0] - x[3] * h[2]) - x[1] / r,
+                       1 / mu * (x[3] * h[1] - x[4] * h[0]) - x[2] / r)
+        e_mag = norm3(e)
+        v_mag = ca.sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5])
+        a = -mu / (v_mag * v_mag - 2.0 * mu / r)
+        inc = ca.acos(h[2] / ca.sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]))
+        n_mag = ca.sqrt(n[0] * n[0] + n[1] * n[1])
+        node = 2 * np.pi - ca.acos(n[0] / n_mag)
+        argp = ca.acos((n[0] * e[0] + n[1] * e[1]) / (n_mag * e_mag))
+        return [(a - a_req) / Re, e_mag - e_req, inc - i_req, node - node_req, argp - argp_req]
+
+    ocp = OCP(n_states=7, n_controls=3, n_phases=4)
+    ocp.dynamics = [make_dynamics(T, q) for T, q in zip(thrust, flow)]
+    ocp.path_constraints = [path] * 4
+    ocp.terminal_costs[3] = lambda xf, tf, x0, t0: -xf[-1] / m_lift
+    ocp.terminal_constraints[3] = orbit
+    vs = np.sqrt(mu / Re)
+    ocp.scale_x = [1 / Re] * 3 + [1 / vs] * 3 + [1 / m_lift]
+    ocp.scale_t = vs / Re
+
+    # guesses: straight line from the pad to the perigee of the target orbit, masses from the burn schedule
+    p_orb = a_req * (1.0 - e_req * e_req)
+    rp = p_orb / (1.0 + e_req)
+    cn, sn, cp, sp, ci, si = (np.cos(node_req), np.sin(node_req), np.cos(argp_req), np.sin(argp_req), np.cos(i_req),
+                              np.sin(i_req))
+    rot = np.array([[cn * cp - sn * sp * ci, -cn * sp - sn * cp * ci, sn * si],
+                    [sn * cp + cn * sp * ci, -sn * sp + cn * cp * ci, -cn * si],
+                    [sp * si, cp * si, ci]])
+    r_end = rot @ np.array([rp, 0.0, 0.0])
+    v_end = rot @ (np.sqrt(mu / p_orb) * np.array([0.0, e_req + 1.0, 0.0]))
+    tk = [0.0, srb_burn, 2 * srb_burn, first_burn, 924.0]
+    start = np.concatenate([r_pad, v_pad, [m_lift]])
+    end = np.concatenate([r_end, v_end, [m_payload + second_dry]])
+    at = lambda t: start + (end - start) / (tk[4] - tk[0]) * (t - tk[0])
+    xs = [start.copy(), at(tk[1]), at(tk[2]), at(tk[3])]
+    xe = [at(tk[1]), at(tk[2]), at(tk[3]), end.copy()]
+    xe[0][-1] = xs[0][-1] - (6 * srb_prop + first_prop / tk[3] * tk[1])
+    xs[1][-1] = xe[0][-1] - 6 * srb_dry
+    xe[1][-1] = xs[1][-1] - (3 * srb_prop + first_prop / tk[3] * (tk[2] - tk[1]))
+    xs[2][-1] = xe[1][-1] - 3 * srb_dry
+    xe[2][-1] = xs[2][-1] - first_prop / tk[3] * (tk[3] - tk[2])
+    xs[3][-1] = xe[2][-1] - first_dry
+    ocp.x00, ocp.xf0 = np.array(xs), np.array(xe)
+    ocp.u00 = np.array([[1, 0, 0], [1, 0, 0], [0, 1, 0], [0, 1, 0]], dtype=float)
+    ocp.uf0 = np.array([[0, 1, 0]] * 4, dtype=float)
+    ocp.t00 = np.array([[t] for t in tk[:4]])
+    ocp.tf0 = np.array([[t] for t in tk[1:]])
+    box_lo, box_hi = [-2 * Re] * 3 + [-10000.0] * 3, [2 * Re] * 3 + [10000.0] * 3
+    ocp.lbx = np.array([box_lo + [xe[k][-1]] for k in range(4)])
+    ocp.ubx = np.array([box_hi + [xs[k][-1]] for k in range(4)])
+    ocp.lbu, ocp.ubu = np.array([[-1.0] * 3] * 4), np.array([[1.0] * 3] * 4)
+    ocp.lbt0 = ocp.ubt0 = np.array([[t] for t in tk[:4]])
+    ocp.lbtf = np.array([[tk[1]], [tk[2]], [tk[3]], [tk[4] - 100]])
+    ocp.ubtf = np.array([[tk[1]], [tk[2]], [tk[3]], [tk[4] + 100]])
+    jumps = [-6 * srb_dry, -3 * srb_dry, -first_dry]
+    ocp.lbe = np.array([[0.0] * 6 + [j] for j in jumps])
+    ocp.ube = ocp.lbe.copy()
+    ocp.validate()
+    return ocp
+
+
 #: problems whose node functors are compiled ahead of time into libmpx.so by build()
 REGISTRY = {
     "moon_lander": moon_lander,
@@ -204,6 +316,7 @@ REGISTRY = {
     "robot_arm": robot_arm,
     "synthetic_6_3": synthetic_6_3,
     "kitchen_sink": kitchen_sink,
+    "delta3_launch_vehicle": delta3_launch_vehicle,
 }
 
 #: uniform polynomial degrees for which build() also compiles the degree-specialised g + jac_g kernel

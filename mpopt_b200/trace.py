@@ -91,13 +91,14 @@ class Expr:
         return NotImplemented
 
     # ---- operators
-    def __add__(self, o): return add(self, o)
+    # a list operand (ca.Vec, what vertcat / slicing return) takes over: scalar (op) vector is element-wise
+    def __add__(self, o): return NotImplemented if isinstance(o, list) else add(self, o)
     def __radd__(self, o): return add(o, self)
-    def __sub__(self, o): return sub(self, o)
+    def __sub__(self, o): return NotImplemented if isinstance(o, list) else sub(self, o)
     def __rsub__(self, o): return sub(o, self)
-    def __mul__(self, o): return mul(self, o)
+    def __mul__(self, o): return NotImplemented if isinstance(o, list) else mul(self, o)
     def __rmul__(self, o): return mul(o, self)
-    def __truediv__(self, o): return div(self, o)
+    def __truediv__(self, o): return NotImplemented if isinstance(o, list) else div(self, o)
     def __rtruediv__(self, o): return div(o, self)
     def __pow__(self, o): return power(self, o)
     def __rpow__(self, o): return power(o, self)

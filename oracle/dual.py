@@ -67,24 +67,32 @@ class Dual:
 
     # -- arithmetic
     def __add__(self, o):
+        if isinstance(o, list):  # scalar (op) vector: the vector's reflected operator applies it element-wise
+            return NotImplemented
         return _add(self, o)
 
     def __radd__(self, o):
         return _add(o, self)
 
     def __sub__(self, o):
+        if isinstance(o, list):  # scalar (op) vector: the vector's reflected operator applies it element-wise
+            return NotImplemented
         return _sub(self, o)
 
     def __rsub__(self, o):
         return _sub(o, self)
 
     def __mul__(self, o):
+        if isinstance(o, list):  # scalar (op) vector: the vector's reflected operator applies it element-wise
+            return NotImplemented
         return _mul(self, o)
 
     def __rmul__(self, o):
         return _mul(o, self)
 
     def __truediv__(self, o):
+        if isinstance(o, list):  # scalar (op) vector: the vector's reflected operator applies it element-wise
+            return NotImplemented
         return _div(self, o)
 
     def __rtruediv__(self, o):

@@ -52,22 +52,30 @@ class Dual2:
         return self
 
     def __add__(self, o):
+        if isinstance(o, list):  # scalar (op) vector: handled element-wise by the vector's reflected operator
+            return NotImplemented
         return _add(self, o, 1.0)
 
     __radd__ = __add__
 
     def __sub__(self, o):
+        if isinstance(o, list):
+            return NotImplemented
         return _add(self, o, -1.0)
 
     def __rsub__(self, o):
         return _add(-self, o, 1.0)
 
     def __mul__(self, o):
+        if isinstance(o, list):
+            return NotImplemented
         return _mul(self, o)
 
     __rmul__ = __mul__
 
     def __truediv__(self, o):
+        if isinstance(o, list):
+            return NotImplemented
         if isinstance(o, Dual2):
             return _mul(self, o._chain(1.0 / o.val, -1.0 / o.val ** 2, 2.0 / o.val ** 3))
         return self._chain(self.val / o, 1.0 / np.asarray(o, dtype=float), None)

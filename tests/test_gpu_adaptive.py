@@ -20,6 +20,7 @@ CASES = [
     ("robot", "robot_arm", 5, 4, "LGR", True),
     ("sink_time_dependent", "kitchen_sink", 5, [3, 4, 6, 2, 5], "LGR", True),
     ("sink_p1", "kitchen_sink", 3, 1, "LGL", True),
+    ("delta3", "delta3_launch_vehicle", 3, [4, 6, 5], "LGR", True),
 ]
 
 
@@ -28,6 +29,8 @@ def _point(n, problem, seed=20261017):
     z = rng.uniform(-1.0, 1.0, n.n_z)
     if problem == "robot_arm":
         z = np.abs(z) + 0.5
+    if problem == "delta3_launch_vehicle":
+        return n.initialize_solution() * (1.0 + 0.01 * rng.standard_normal(n.n_z))
     for ph in range(n.P):
         z[n.colT0(ph)] = 0.3 + 0.25 * ph
         z[n.colTF(ph)] = 2.0 + 1.5 * ph

@@ -29,6 +29,8 @@ CASES = [
     ("hyper_p50", "hyper_sensitive", 5, 50, "LGR", False),   # docs/source/notebooks/hypersensitive.ipynb:165-170 (v1 kernel: degree > 31)
     ("vdp_p25", "van_der_pol", 1, 25, "LGR", False),          # vanderpol.ipynb:177-182
     ("moon_p40_mixed", "moon_lander", 3, [40, 6, 33], "LGL", True),
+    ("delta3_p11", "delta3_launch_vehicle", 1, 11, "LGR", False),   # multi_stage_launch_vehicle_ascent.ipynb:466-471
+    ("delta3_mixed", "delta3_launch_vehicle", 4, [4, 6, 5, 3], "LGL", True),
 ]
 
 
@@ -68,6 +70,8 @@ def _point(ora, problem, dirichlet):
     z, p = random_point(ora, dirichlet=dirichlet)
     if problem == "robot_arm":
         z = np.abs(z) + 0.5  # keep sin(x4) and the inertia terms away from zero
+    if problem == "delta3_launch_vehicle":  # stay near the ascent trajectory: |r| ~ Re, acos arguments inside (-1, 1)
+        z = ora.initialize_solution() * (1.0 + 0.01 * np.random.default_rng(7).standard_normal(ora.n_z))
     return z, p
 
 

@@ -26,6 +26,7 @@ BANNERS = [
     ("hyper_sensitive", 5, 50, "LGR", (501, 252, 0)),  # hypersensitive.ipynb:165-170
     ("van_der_pol", 1, 25, "LGR", (76, 52, 25)),       # vanderpol.ipynb:177-182
     ("two_phase_schwartz", 1, 20, "LGR", (125, 88, 41)),  # twophaseschwartz.ipynb:195-200
+    ("delta3_launch_vehicle", 1, 11, "LGR", (474, 374, 276)),  # multi_stage_launch_vehicle_ascent.ipynb:466-471
 ]
 
 
@@ -106,3 +107,26 @@ def test_exact_zero_folding_switch():
         assert len(b.structure()[1]) - len(a.structure()[1]) == 2
     else:
         assert len(b.structure()[1]) == len(a.structure()[1])
+
+
+def test_delta3_banner_bound_types_and_derivatives():
+    """The 4-phase launch-vehicle NLP: IPOPT's banner also counts the bound types (all 474 free variables boxed, 132
+    two-sided and 144 upper-only inequalities, multi_stage_launch_vehicle_ascent.ipynb:467-474); the Jacobian and the
+    gradient of the scaled problem agree with finite differences near the example's initial guess."""
+    n = OracleNLP(pr.delta3_launch_vehicle(), 1, 11, "LGR")
+    zmin, zmax, gmin, gmax = n.bounds()
+    free = zmin != zmax
+    assert int((free & np.isfinite(zmin) & np.isfinite(zmax)).sum()) == 474
+    ineq = gmin != gmax
+    assert int((ineq & np.isfinite(gmin) & np.isfinite(gmax)).sum()) == 132
+    assert int((ineq & ~np.isfinite(gmin) & np.isfinite(gmax)).sum()) == 144
+    z = n.initialize_solution() * (1.0 + 0.01 * np.random.default_rng(5).standard_normal(n.n_z))
+    J = n.jac_g(z).toarray()
+    gr = n.grad_f(z)
+    for j in np.random.default_rng(6).choice(n.n_z, 60, replace=False):
+        e = np.zeros(n.n_z)
+        e[j] = 1e-6 * max(1.0, abs(z[j]))
+        fd = (n.g(z + e) - n.g(z - e)) / (2 * e[j])
+        assert np.abs(fd - J[:, j]).max() < 2e-6 * max(1.0, np.abs(J[:, j]).max()), j
+        fdf = (n.f(z + e) - n.f(z - e)) / (2 * e[j])
+        assert abs(fdf - gr[j]) < 2e-6 * max(1.0, abs(gr[j])), j
