@@ -305,6 +305,122 @@ def delta3_launch_vehicle(drag=0.0):
     return ocp
 
 
+def falcon9_launcher(drag=0.0, dyn_pressure=0.0, glide_slope=0.0):
+    """Falcon 9 to orbit with booster return: 7 states, 4 controls (thrust direction + throttle), 3 phases linked as a
+    FORK -- ascent (0) -> second stage to orbit (1) and ascent (0) -> booster return (2) -- with different path rows
+    per phase (3, 3, 5), two of phase 2's rows constant while the dynamic-pressure and glide-slope switches are off.
+
+    Restates the OCP of the reference's examples/Multi-phase/falcon9_launcher.py:35-304; the IPOPT banner of
+    docs/source/notebooks/falcon9_to_orbit.ipynb:480-485 (956 variables, 746 equalities, 641 inequalities at five
+    segments of degree 6) pins the fork's event rows and the mid-point rows whose bounds coincide (fixed throttle)."""
+    Re, mu, g0 = 6378145.0, 3.986012e14, 9.80665
+    rho0, scale_h, area_cd = 1.225, 7200.0, 4 * np.pi * 0.5
+    lat = 28.5 * np.pi / 180.0
+    pad = np.array([Re * np.cos(lat), 0.0, Re * np.sin(lat)])
+    m_lift = 431.6e3 + 107.5e3
+    m_final = 107.5e3 - 103.5e3
+    booster_dry = 431.6e3 - 409.5e3
+    start = np.concatenate([pad, 7.29211585e-5 * np.array([0.1, 0.1, 0.1]), [m_lift]])
+    q_max, isp = 80e3, 340.0
+    thrust = [9 * 934.0e3, 934.0e3, 934.0e3]
+
+    def norm3(v):
+        return ca.sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2])
+
+    def make_dynamics(T):
+        def f(x, u, t):
+            r, v, m = x[:3], x[3:6], x[6]
+            rm = norm3(r)
+            rho = rho0 * ca.exp(-(rm - Re) / scale_h)
+            D = -rho / (2 * m) * area_cd * norm3(v) * v
+            grav = -mu / (rm * rm * rm) * r
+            return ([x[3], x[4], x[5]] + [T * u[3] / m * u[i] + drag * D[i] + grav[i] for i in range(3)]
+                    + [-T * u[3] / (isp * g0)])
+        return f
+
+    def path_ascent(x, u, t):
+        uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2]
+        return [uu - 1, -uu + 1, -norm3(x) / Re + 1]
+
+    def path_return(x, u, t):
+        rho = rho0 * ca.exp(-(norm3(x) - Re) / scale_h)
+        v_sq = x[3] * x[3] + x[4] * x[4] + x[5] * x[5]
+        rel = ca.vertcat(x[0] - start[0], x[1] - start[1], x[2] - start[2])
+        uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2]
+        cone = norm3(rel) * np.cos(80.0 * np.pi / 180.0) - (rel[0] * start[0] + rel[1] * start[1] + rel[2] * start[2]) / np.sqrt(
+            start[0] ** 2 + start[1] ** 2 + start[2] ** 2)
+        return [dyn_pressure * 0.5 * rho * v_sq / q_max - 1.0, uu - 1, -uu + 1, -norm3(x) / Re + 1, glide_slope * cone]
+
+    a_req, e_req, i_req = 6593145.0, 0.0076, 28.5 * np.pi / 180.0
+    node_req, argp_req = 269.8 * np.pi / 180.0, 130.5 * np.pi / 180.0
+
+    def orbit(x, t, x0, t0):
+        h = ca.vertcat(x[1] * x[5] - x[4] * x[2], x[3] * x[2] - x[0] * x[5], x[0] * x[4] - x[1] * x[3])
+        n = ca.vertcat(-h[1], h[0], 0)
+        r = norm3(x)
+        e = ca.vertcat(1 / mu * (x[4] * h[2] - x[5] * h[1]) - x[0] / r,
+                       1 / mu * (x[5] * h[0] - x[3] * h[2]) - x[1] / r,
+                       1 / mu * (x[3] * h[1] - x[4] * h[0]) - x[2] / r)
+        e_mag = norm3(e)
+        v_mag = ca.sqrt(x[3] * x[3] + x[4] * x[4] + x[5] * x[5])
+        a = -mu / (v_mag * v_mag - 2.0 * mu / r)
+        inc = ca.acos(h[2] / ca.sqrt(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]))
+        n_mag = ca.sqrt(n[0] * n[0] + n[1] * n[1])
+        node = 2 * np.pi - ca.acos(n[0] / n_mag)
+        argp = ca.acos((n[0] * e[0] + n[1] * e[1]) / (n_mag * e_mag))
+        return [(a - a_req) / Re, e_mag - e_req, inc - i_req, node - node_req, argp - argp_req]
+
+    vs = np.sqrt(mu / Re)
+
+    def back_to_pad(x, t, x_0, t_0):
+        return [(x[i] - start[i]) / Re for i in range(3)] + [(x[i] - start[i]) / vs for i in range(3, 6)]
+
+    ocp = OCP(n_states=7, n_controls=4, n_phases=3)
+    ocp.dynamics = [make_dynamics(T) for T in thrust]
+    ocp.path_constraints = [path_ascent, path_ascent, path_return]
+    ocp.terminal_costs[1] = lambda xf, tf, x0, t0: -xf[6] / m_lift
+    ocp.terminal_constraints[1] = orbit
+    ocp.terminal_constraints[2] = back_to_pad
+    ocp.scale_x = np.array([1 / Re] * 3 + [1 / vs] * 3 + [1 / m_lift])
+    ocp.scale_t = vs / Re
+
+    p_orb = a_req * (1.0 - e_req * e_req)
+    cn, sn, cp, sp, ci, si = (np.cos(node_req), np.sin(node_req), np.cos(argp_req), np.sin(argp_req), np.cos(i_req),
+                              np.sin(i_req))
+    rot = np.array([[cn * cp - sn * sp * ci, -cn * sp - sn * cp * ci, sn * si],
+                    [sn * cp + cn * sp * ci, -sn * sp + cn * cp * ci, -cn * si],
+                    [sp * si, cp * si, ci]])
+    end = np.concatenate([rot @ np.array([p_orb / (1.0 + e_req), 0.0, 0.0]),
+                          rot @ (np.sqrt(mu / p_orb) * np.array([0.0, e_req + 1.0, 0.0])), [m_final]])
+    t_sep, t_orbit, t_land = 131.4, 453.4, 569.7
+    at_sep = start + (end - start) / t_orbit * t_sep
+    burnt = 9 * 934e3 / (isp * g0) * t_sep
+    sep_end = at_sep.copy()
+    sep_end[-1] = start[-1] - burnt
+    left_in_booster = 409.5e3 - burnt
+    second_start = at_sep.copy()
+    second_start[-1] = sep_end[-1] - (booster_dry + left_in_booster)
+    ocp.x00 = np.array([start, second_start, sep_end])
+    ocp.xf0 = np.array([sep_end, end, start])
+    ocp.u00 = np.array([[1, 0, 0, 1.0], [1, 0, 0, 1], [0, 1, 0, 1]])
+    ocp.uf0 = np.array([[0, 1, 0, 1.0], [0, 1, 0, 1], [1, 0, 0, 0.5]])
+    ocp.t00 = np.array([[0.0], [t_sep], [t_sep]])
+    ocp.tf0 = np.array([[t_sep], [t_orbit], [t_land]])
+    box_lo, box_hi = [-2 * Re] * 3 + [-10000.0] * 3, [2 * Re] * 3 + [10000.0] * 3
+    ocp.lbx = np.array([box_lo + [sep_end[-1]], box_lo + [end[-1]], box_lo + [booster_dry]])
+    ocp.ubx = np.array([box_hi + [start[-1]], box_hi + [107.5e3], box_hi + [sep_end[-1] - 107.5e3]])
+    ocp.lbu = np.array([[-1.0, -1.0, -1.0, 1.0], [-1.0, -1.0, -1.0, 1.0], [-1.0, -1.0, -1.0, 0.38]])
+    ocp.ubu = np.array([[1.0] * 4] * 3)
+    ocp.lbt0 = ocp.ubt0 = np.array([[0.0], [t_sep], [t_sep]])
+    ocp.lbtf = np.array([[t_sep], [t_orbit - 50], [t_land - 100]])
+    ocp.ubtf = np.array([[t_sep], [t_orbit + 50], [t_land + 100]])
+    ocp.lbe = np.array([[0.0] * 6 + [-(booster_dry + left_in_booster)], [0.0] * 6 + [-107.5e3]])
+    ocp.ube = ocp.lbe.copy()
+    ocp.phase_links = [(0, 1), (0, 2)]
+    ocp.validate()
+    return ocp
+
+
 #: problems whose node functors are compiled ahead of time into libmpx.so by build()
 REGISTRY = {
     "moon_lander": moon_lander,
@@ -317,6 +433,7 @@ REGISTRY = {
     "synthetic_6_3": synthetic_6_3,
     "kitchen_sink": kitchen_sink,
     "delta3_launch_vehicle": delta3_launch_vehicle,
+    "falcon9_launcher": falcon9_launcher,
 }
 
 #: uniform polynomial degrees for which build() also compiles the degree-specialised g + jac_g kernel

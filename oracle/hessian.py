@@ -21,11 +21,12 @@ from __future__ import annotations
 import numpy as np
 import scipy.sparse as sp
 
+from .dual import Vec
 from .dual2 import Dual2
 
 
-class _V(list):
-    """What the user callables index as x[i] / u[i] / a[i]."""
+class _V(Vec):
+    """What the user callables index as x[i] / u[i] / a[i] (slices and scalar x vector products included)."""
 
 
 def _components(out, n):

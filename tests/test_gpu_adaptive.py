@@ -21,6 +21,7 @@ CASES = [
     ("sink_time_dependent", "kitchen_sink", 5, [3, 4, 6, 2, 5], "LGR", True),
     ("sink_p1", "kitchen_sink", 3, 1, "LGL", True),
     ("delta3", "delta3_launch_vehicle", 3, [4, 6, 5], "LGR", True),
+    ("falcon9", "falcon9_launcher", 2, [5, 3], "LGR", True),
 ]
 
 
@@ -29,7 +30,7 @@ def _point(n, problem, seed=20261017):
     z = rng.uniform(-1.0, 1.0, n.n_z)
     if problem == "robot_arm":
         z = np.abs(z) + 0.5
-    if problem == "delta3_launch_vehicle":
+    if problem in ("delta3_launch_vehicle", "falcon9_launcher"):
         return n.initialize_solution() * (1.0 + 0.01 * rng.standard_normal(n.n_z))
     for ph in range(n.P):
         z[n.colT0(ph)] = 0.3 + 0.25 * ph

@@ -31,6 +31,8 @@ CASES = [
     ("moon_p40_mixed", "moon_lander", 3, [40, 6, 33], "LGL", True),
     ("delta3_p11", "delta3_launch_vehicle", 1, 11, "LGR", False),   # multi_stage_launch_vehicle_ascent.ipynb:466-471
     ("delta3_mixed", "delta3_launch_vehicle", 4, [4, 6, 5, 3], "LGL", True),
+    ("falcon9_5x6", "falcon9_launcher", 5, 6, "LGR", False),        # falcon9_to_orbit.ipynb:480-485: fork links, constant path rows
+    ("falcon9_mixed", "falcon9_launcher", 3, [7, 2, 5], "CGL", True),
 ]
 
 
@@ -70,7 +72,7 @@ def _point(ora, problem, dirichlet):
     z, p = random_point(ora, dirichlet=dirichlet)
     if problem == "robot_arm":
         z = np.abs(z) + 0.5  # keep sin(x4) and the inertia terms away from zero
-    if problem == "delta3_launch_vehicle":  # stay near the ascent trajectory: |r| ~ Re, acos arguments inside (-1, 1)
+    if problem in ("delta3_launch_vehicle", "falcon9_launcher"):  # stay near the ascent trajectory: |r| ~ Re, acos arguments inside (-1, 1)
         z = ora.initialize_solution() * (1.0 + 0.01 * np.random.default_rng(7).standard_normal(ora.n_z))
     return z, p
 
@@ -387,7 +389,9 @@ def test_interpolation_and_residuals_match_oracle(libmpx, problem, K, po, scheme
                                                  ("two_phase_schwartz", 4, 6, "LGR"), ("van_der_pol", 3, [2, 5, 3], "CGL"),
                                                  ("robot_arm", 7, 5, "LGR"), ("synthetic_6_3", 33, 15, "LGR"),
                                                  ("hyper_sensitive", 3, 9, "LGL"), ("generic_two_phase", 3, [2, 5, 3], "CGL"),
-                                                 ("hyper_sensitive", 2, [40, 7], "LGR")])
+                                                 ("hyper_sensitive", 2, [40, 7], "LGR"),
+                                                 ("delta3_launch_vehicle", 2, [5, 4], "LGR"),
+                                                 ("falcon9_launcher", 3, 4, "LGR")])
 def test_lagrangian_hessian_matches_oracle(libmpx, problem, K, po, scheme):
     """nlp_hess_l(x, p, lam_f, lam_g) -- lower triangle, CSR -- against the oracle's second-order
     dual-number restatement: pattern bit-exact, values to 1e-10."""
@@ -399,6 +403,8 @@ def test_lagrangian_hessian_matches_oracle(libmpx, problem, K, po, scheme):
     tr = Transcription(REGISTRY[problem](), K, po, scheme)
     ora = OracleNLP(REGISTRY[problem](), K, po, scheme)
     z, p = random_point(ora, dirichlet=True)
+    if problem in ("delta3_launch_vehicle", "falcon9_launcher"):  # near the ascent trajectory (orbital-element terminal rows: acos, 1/|e|)
+        z = ora.initialize_solution() * (1.0 + 0.01 * np.random.default_rng(7).standard_normal(ora.n_z))
     rng = np.random.default_rng(4)
     lam, sig = rng.uniform(-1, 1, ora.n_g), 0.6
     H = hess_l(ora, z, p, sig, lam)

@@ -10,12 +10,15 @@ from oracle.nlp import OracleNLP
 
 @pytest.mark.parametrize("problem,K,po,scheme", [("moon_lander", 3, 3, "LGR"), ("kitchen_sink", 3, [3, 2, 4], "LGL"),
                                                  ("two_phase_schwartz", 2, 4, "LGR"), ("van_der_pol", 3, [2, 5, 3], "CGL"),
-                                                 ("robot_arm", 2, 3, "LGR"), ("synthetic_6_3", 2, 4, "LGR")])
+                                                 ("robot_arm", 2, 3, "LGR"), ("synthetic_6_3", 2, 4, "LGR"),
+                                                 ("delta3_launch_vehicle", 1, 3, "LGR")])
 def test_hessian_by_finite_differences(problem, K, po, scheme):
     from mpopt_b200.problems import REGISTRY
 
     ora = OracleNLP(REGISTRY[problem](), K, po, scheme)
     z, p = random_point(ora, dirichlet=True)
+    if problem == "delta3_launch_vehicle":
+        z = ora.initialize_solution() * (1.0 + 0.01 * np.random.default_rng(7).standard_normal(ora.n_z))
     rng = np.random.default_rng(9)
     lam, sig = rng.uniform(-1, 1, ora.n_g), 0.7
     H = hess_l(ora, z, p, sig, lam)

@@ -27,6 +27,7 @@ BANNERS = [
     ("van_der_pol", 1, 25, "LGR", (76, 52, 25)),       # vanderpol.ipynb:177-182
     ("two_phase_schwartz", 1, 20, "LGR", (125, 88, 41)),  # twophaseschwartz.ipynb:195-200
     ("delta3_launch_vehicle", 1, 11, "LGR", (474, 374, 276)),  # multi_stage_launch_vehicle_ascent.ipynb:466-471
+    ("falcon9_launcher", 5, 6, "LGR", (956, 746, 641)),       # falcon9_to_orbit.ipynb:480-485 (fork: links (0,1), (0,2))
 ]
 
 
