@@ -185,7 +185,7 @@ def _mul(a, b):
     if not isinstance(b, Dual2):
         c = np.asarray(b, dtype=float)
         if c.ndim == 0 and float(c) == 0.0:
-            return Dual2(np.zeros_like(a.val))  # SX folds 0 * x -> 0
+            return 0.0  # SX folds 0 * x -> 0: a plain constant, so that later products with it fold too
         return a._chain(a.val * c, c, None)
     g = {k: b.val * d for k, d in a.g.items()}
     for k, d in b.g.items():
