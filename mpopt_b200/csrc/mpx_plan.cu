@@ -220,6 +220,7 @@ struct mpx_plan {
   DevBuf d_dmid, d_seg_dmid, d_wpart, d_seg_rpre;  // d_seg_rpre: [P][K]
   DevBuf d_ticket;                                 // [P] arrival counters of the single-launch f + grad_f kernel
   int smem_adapt = 0;
+  std::vector<int> adapt_img;              // per phase: doubles of a staged residual-row image (0: direct stores)
   std::vector<int64_t> sw_direct;          // per phase: CSR position of the SW block when it is written in place, else -1
   std::vector<int64_t> gather_runs;        // (first, count) CSR ranges that go through the gather (empty: everything)
   int64_t nvar, n_z, n_p, n_g, nnz_full, nnz;
@@ -1191,8 +1192,23 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     }
     const int n1 = dmax + 1;  // same formula as mpx_adapt_smem_doubles
     p.smem_adapt = 8 * (MpxTab::pad2(n1) + 2 * MpxTab::pad2(dmax * n1) + MpxTab::pad2((nx + nu) * n1) +
-                        MpxTab::pad2(dmax * (3 * nx + njf + 2)) + MpxTab::pad2(dmax * (2 * nx + nu)));
+                        MpxTab::pad2(dmax * (3 * nx + njf + 2)) + MpxTab::pad2(dmax * (2 * nx + nu)) + MPX_THREADS);
     if (p.smem_adapt > 227 * 1024) return fail(MPX_ELIMIT, "polynomial degree too large for the adaptive NLP kernel");
+    // residual-row images for the bulk-copy engine: two per CTA, when no row carries the K-wide width block of
+    // time-dependent dynamics and a CTA stays below ~1/3 of an SM's shared memory (MPX_ADAPT_STAGE=0: direct stores)
+    p.adapt_img.assign(p.P, 0);
+    const char* se = getenv("MPX_ADAPT_STAGE");
+    for (int ph = 0; ph < p.P && p.mid_res && !(se && atoi(se) == 0); ++ph) {
+      const PhaseLayout& L = p.ph[ph];
+      bool ft = false;
+      int img = 0;
+      for (int s = 0; s < nx; ++s) {
+        ft |= L.f_t[s] != 0;
+        img = std::max(img, dmax * ((dmax + 1) * L.res_nblk[s] + 2 * L.f_nz[s] + L.res_na[s] + 1));
+      }
+      img = MpxTab::pad2(img);
+      if (!ft && p.smem_adapt + 2 * (img + 2) * 8 <= 76 * 1024) p.adapt_img[ph] = img;
+    }
   }
   build_structure(p);
   if (!p.gather.empty()) CUDA_TRY(up(p.d_gather, p.gather.data(), p.gather.size() * sizeof(int64_t)));
@@ -1398,6 +1414,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     a.ist = 1.0 / a.st, a.idelta = 1.0 / a.delta;
     if (p.adaptive) {
       a.ad_sw_u = L.sw_u, a.ad_sw_x = L.sw_x, a.ad_res = p.mid_res;
+      a.ad_img = p.adapt_img[ph];
       a.dmid = p.d_dmid.as<double>(), a.seg_dmid = p.d_seg_dmid.as<int32_t>();
       a.seg_rpre = p.d_seg_rpre.as<int64_t>() + (int64_t)ph * K;
       for (int s = 0; s < nx; ++s) a.eF[s] = L.eF[s];
@@ -1566,7 +1583,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     if (p.adaptive) {  // SW rows and the d/dw entries, staged behind the base kernels' values
       a.ad_jac = jac ? 1 : 0, a.ext = jac ? p.d_full.as<double>() + p.n_base : nullptr;
       a.ext_sw = !jac ? nullptr : (p.sw_direct[ph] >= 0 ? d_vals + p.sw_direct[ph] - L.eSum : a.ext);
-      CUDA_TRY(p.prog->phases[ph]->adapt(a, p.K, (size_t)p.smem_adapt, st));
+      CUDA_TRY(p.prog->phases[ph]->adapt(a, p.K, (size_t)p.smem_adapt + (jac ? 2 * (size_t)(a.ad_img + 2) * 8 : 0), st));
       ++p.launches;
     }
     if (L.has_dU) {
