@@ -16,9 +16,14 @@
 #include "../../include/mpx.h"
 
 namespace {
+// the parameter vector may be NULL when the NLP has none (adaptive NLP: the widths are part of x, n_p = 0)
+bool p_missing(mpx_plan* plan, const double* p) {
+  int64_t n_p = 0;
+  return !p && (mpx_sizes(plan, nullptr, &n_p, nullptr, nullptr) != MPX_OK || n_p != 0);
+}
 // one fused evaluation per distinct x: stage everything on new_x, then only fetch
 int ensure_staged(mpx_ipopt_data* d, const double* x, int new_x, int need) {
-  if (!d || !d->plan || !d->p) return MPX_EINVAL;
+  if (!d || !d->plan || p_missing(d->plan, d->p)) return MPX_EINVAL;
   if ((new_x & 0xff) || (mpx_staged(d->plan) & need) != need)
     return mpx_stage(d->plan, x, d->p, MPX_STAGE_F | MPX_STAGE_GRAD | MPX_STAGE_G | MPX_STAGE_JAC);
   return MPX_OK;
@@ -72,7 +77,7 @@ extern "C" int mpx_ipopt_eval_h(int n, const double* x, int new_x, double obj_fa
                                 int new_lambda, int nele_hess, int* iRow, int* jCol, double* values, void* user_data) {
   (void)new_x, (void)new_lambda;  // the Hessian kernel is cheap next to the Jacobian: always evaluated from (x, lambda)
   mpx_ipopt_data* d = static_cast<mpx_ipopt_data*>(user_data);
-  if (!d || !d->plan || !d->p || !sizes_ok(d->plan, n, m, -1)) return 0;
+  if (!d || !d->plan || p_missing(d->plan, d->p) || !sizes_ok(d->plan, n, m, -1)) return 0;
   int64_t nnz = 0;
   if (mpx_hess_structure(d->plan, &nnz, nullptr, nullptr) != MPX_OK || nnz != nele_hess) return 0;
   if (!values) {
@@ -137,7 +142,7 @@ extern "C" int mpx_casadi_bind(mpx_plan* plan) {
 namespace {
 // kinds: 0 nlp_f, 1 nlp_g, 2 nlp_grad_f, 3 nlp_jac_g
 int ca_eval(int kind, const double** arg, double** res) {
-  if (!B.plan || !arg || !res || !arg[0] || !arg[1]) return 1;
+  if (!B.plan || !arg || !res || !arg[0] || p_missing(B.plan, arg[1])) return 1;
   const int what = kind == 0 ? MPX_STAGE_F : kind == 1 ? MPX_STAGE_G : kind == 2 ? (MPX_STAGE_F | MPX_STAGE_GRAD)
                                                                                  : (MPX_STAGE_G | MPX_STAGE_JAC);
   if (mpx_stage(B.plan, arg[0], arg[1], what) != MPX_OK) return 1;
@@ -200,7 +205,7 @@ MPX_CASADI_DEFINE(nlp_jac_g, 3, 2)
 
 // nlp_hess_l (x, p, lam_f, lam_g) -> (hess_gamma_x_x): triu of the Lagrangian Hessian in CCS
 extern "C" int nlp_hess_l(const double** arg, double** res, long long*, double*, int) {
-  if (!B.plan || B.sp_hess.empty() || !arg || !res || !arg[0] || !arg[1] || !arg[2] || !arg[3]) return 1;
+  if (!B.plan || B.sp_hess.empty() || !arg || !res || !arg[0] || p_missing(B.plan, arg[1]) || !arg[2] || !arg[3]) return 1;
   if (!res[0]) return 0;
   return mpx_eval_hess_l(B.plan, arg[0], arg[1], arg[2][0], arg[3], res[0]) == MPX_OK ? 0 : 1;
 }

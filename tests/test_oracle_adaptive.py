@@ -81,3 +81,23 @@ def test_structure_is_point_independent_and_has_no_spurious_entries():
     assert np.array_equal(J1.indptr, J2.indptr) and np.array_equal(J1.indices, J2.indices)
     # every structural entry is non-zero at (at least one of) two generic points
     assert ((J1.data != 0) | (J2.data != 0)).all()
+
+
+def test_host_layout_agrees_with_oracle():
+    """The Python twin of the plan's layout (mpopt_b200/layout.py, no GPU): variables, rows and the width columns of
+    the adaptive NLP sit where the oracle puts them."""
+    from mpopt_b200.layout import Layout
+    from mpopt_b200.program import Program
+
+    for name, K, po in (("moon_lander", 3, [3, 3, 3]), ("kitchen_sink", 3, [3, 2, 4]), ("falcon9_launcher", 2, [5, 3])):
+        ocp = pr.REGISTRY[name]()
+        ora = OracleAdaptiveNLP(ocp, K, po, "LGR")
+        sw_u = [ora._rows[ph]["sw_u"] for ph in range(ora.P)]
+        sw_x = [ora._rows[ph]["sw_x"] for ph in range(ora.P)]
+        L = Layout(Program(ocp), po, [bool(v) for v in ocp.diff_u], [False] * ora.P, [False] * ora.P,
+                   ora.n_links, adaptive=dict(sw_u=sw_u, sw_x=sw_x, mid_residuals=True))
+        assert (L.n_z, L.n_p, L.n_g) == (ora.n_z, 0, ora.n_g)
+        for ph in range(ora.P):
+            assert L.phases[ph].gSW == ora.row_off[ph] + ora._rows[ph]["SW"]
+            assert L.phases[ph].gTC == ora.row_off[ph] + ora._rows[ph]["TC"]
+            assert L.colW(ph, K - 1) == ora.colW(ph, K - 1) and L.colT0(ph) == ora.colT0(ph)

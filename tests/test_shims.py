@@ -157,3 +157,55 @@ def test_casadi_externals_match_oracle(libmpx):
         assert_close(hv, H.data, "nlp_hess_l")
     finally:
         libmpx.mpx_casadi_bind(None)
+
+
+@pytest.mark.gpu
+def test_shims_with_the_adaptive_nlp(libmpx):
+    """mpopt_adaptive's NLP has no parameters (mpopt.py:3190-3191): both solver interfaces accept p = NULL for such a
+    plan, report n_p = 0 and return the widths-as-variables g / jac_g / grad_f; the Hessian callback reports failure."""
+    from mpopt_b200 import _lib
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import van_der_pol
+    from oracle.adaptive import OracleAdaptiveNLP
+
+    po = [3, 5, 2, 4]
+    tr = Transcription(van_der_pol(), 4, po, "LGR", adaptive=True, drop_exact_zeros=False)
+    ora = OracleAdaptiveNLP(van_der_pol(), 4, po, "LGR", drop_exact_zeros=False)
+    rng = np.random.default_rng(11)
+    z = rng.uniform(-1, 1, ora.n_z)
+    z[ora.colT0(0)], z[ora.colTF(0)] = 0.0, 5.0
+    z[ora.colW(0, np.arange(4))] = rng.dirichlet(np.ones(4))
+    n, m, nnz = tr.n_z, tr.n_g, tr.nnz
+    J = ora.jac_g(z)
+    # IPOPT C interface, user_data.p = NULL
+    d = _lib.IpoptData(tr._plan, None)
+    ud = C.byref(d)
+    f, grad, g, vals = np.zeros(1), np.zeros(n), np.zeros(m), np.zeros(nnz)
+    assert libmpx.mpx_ipopt_eval_f(n, _lib.ptr(z), 1, _lib.ptr(f), ud) == 1
+    assert libmpx.mpx_ipopt_eval_grad_f(n, _lib.ptr(z), 0, _lib.ptr(grad), ud) == 1
+    assert libmpx.mpx_ipopt_eval_g(n, _lib.ptr(z), 0, m, _lib.ptr(g), ud) == 1
+    assert libmpx.mpx_ipopt_eval_jac_g(n, _lib.ptr(z), 0, m, nnz, None, None, _lib.ptr(vals), ud) == 1
+    assert abs(f[0] - ora.f(z)) <= 1e-10 * max(1.0, abs(ora.f(z)))
+    assert_close(grad, ora.grad_f(z), "grad_f")
+    assert_close(g, ora.g(z), "g")
+    assert_close(vals, J.data, "jac_g values")
+    lam = np.zeros(m)
+    assert libmpx.mpx_ipopt_eval_h(n, _lib.ptr(z), 0, 1.0, m, _lib.ptr(lam), 1, 1, None, None, _lib.ptr(vals), ud) == 0
+    # CasADi external functions, arg[1] = NULL, p declared with zero rows
+    assert libmpx.mpx_casadi_bind(tr._plan) == 0
+    try:
+        libmpx.nlp_g_sparsity_in.restype = C.POINTER(C.c_longlong)
+        libmpx.nlp_g_sparsity_in.argtypes = [C.c_longlong]
+        sp_p = libmpx.nlp_g_sparsity_in(1)
+        assert sp_p[0] == 0
+        arg = (C.POINTER(C.c_double) * 2)(_lib.ptr(z), None)
+        g[:] = 0
+        jv = np.zeros(nnz)
+        res = (C.POINTER(C.c_double) * 2)(_lib.ptr(g), _lib.ptr(jv))
+        assert libmpx.nlp_jac_g(arg, res, None, None, 0) == 0
+        Jc = J.tocsc()
+        Jc.sort_indices()
+        assert_close(g, ora.g(z), "nlp_jac_g: g")
+        assert_close(jv, Jc.data, "nlp_jac_g: jac_g_x (CCS order)")
+    finally:
+        libmpx.mpx_casadi_bind(None)
