@@ -17,20 +17,17 @@ def _cases():
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(sys_path_golden, "make_golden.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
-    return m.CASES
+    return m
 
 
-CASES = _cases()
+_M = _cases()
+CASES = _M.CASES
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_oracle_reproduces_golden(name):
-    from mpopt_b200.problems import REGISTRY
-    from oracle.nlp import OracleNLP
-
-    problem, K, po, scheme = CASES[name]
     G = np.load(os.path.join(sys_path_golden, name + ".npz"))
-    ora = OracleNLP(REGISTRY[problem](), K, po, scheme, drop_exact_zeros=False)
+    ora, _, _ = _M.build(CASES[name])
     f, g, grad, J = ora._eval(G["z"], G["p"])
     assert np.array_equal(J.indptr, G["rowptr"]) and np.array_equal(J.indices, G["colind"])
     assert_close(J.data, G["values"], "values", 1e-13)
@@ -47,9 +44,9 @@ def test_cuda_reproduces_golden(libmpx, name):
     from mpopt_b200.nlp import Transcription
     from mpopt_b200.problems import REGISTRY
 
-    problem, K, po, scheme = CASES[name]
+    problem, K, po, scheme = CASES[name][:4]
     G = np.load(os.path.join(sys_path_golden, name + ".npz"))
-    tr = Transcription(REGISTRY[problem](), K, po, scheme, drop_exact_zeros=False)
+    tr = Transcription(REGISTRY[problem](), K, po, scheme, drop_exact_zeros=False, adaptive=len(CASES[name]) > 4)
     rp, ci = tr.structure()
     assert np.array_equal(rp, G["rowptr"]) and np.array_equal(ci, G["colind"])  # bit-exact index work
     g = np.empty(tr.n_g)
