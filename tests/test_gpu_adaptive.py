@@ -178,23 +178,6 @@ def test_hyper_sensitive_h_adaptive_solve(mp):
     _check_post(mpo, sol)
 
 
-def test_h_adaptive_static_helpers(mp):
-    H = mp.mpopt_h_adaptive
-    # equal residual everywhere -> equal widths
-    w = H.get_roots_wrt_equal_area(np.ones(21), 4)
-    assert np.allclose(w, 0.25)
-    # two good segments merge, the bad one is split in two
-    w = H.merge_split_segments_based_on_residuals([1e-6, 1e-6, 1.0], [0.25, 0.25, 0.5], ERR_TOL=1e-3)
-    assert np.allclose(w, [0.5, 0.25, 0.25])
-    # nothing to merge: unchanged
-    w0 = [0.5, 0.5]
-    assert H.merge_split_segments_based_on_residuals([1.0, 1e-6], w0, ERR_TOL=1e-3) is w0
-    w = H.compute_segment_widths_at_times(np.array([1.0, 3.0]), 3, 0.0, 4.0)
-    assert np.allclose(w, [0.25, 0.5, 0.25])
-    w = H.compute_segment_widths_at_times(np.array([2.0]), 4, 0.0, 4.0)
-    assert abs(w.sum() - 1) < 1e-12 and len(w) == 4
-
-
 def test_moon_lander_mpopt_adaptive_solve(mp):
     """tests/test_mpopt.py:258-259, :473-483."""
     from mpopt_b200.problems import moon_lander
