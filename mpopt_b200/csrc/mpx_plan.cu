@@ -1644,7 +1644,7 @@ static int launch_f_grad(mpx_plan& p, const double* d_z, const double* d_p, doub
       ++p.launches;
     }
     if (p.adaptive && grad) {  // d f / d w (mpopt.py:2945: the widths are part of x)
-      CUDA_TRY(p.prog->phases[ph]->adapt_grad(a, (p.K + MPX_THREADS - 1) / MPX_THREADS, p.ph[ph].cost_t, st));
+      CUDA_TRY(p.prog->phases[ph]->adapt_grad(a, (p.K + MPX_THREADS / 32 - 1) / (MPX_THREADS / 32), p.ph[ph].cost_t, st));
       p.launches += p.ph[ph].cost_t ? 2 : 1;
     }
   }
