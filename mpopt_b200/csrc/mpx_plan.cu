@@ -447,7 +447,8 @@ RtApi& rt_api() {
 struct MpxRtPhase final : MpxPhaseKernels {
   CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_gjac4[2] = {nullptr, nullptr},
                f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr}, f_resid[2] = {nullptr, nullptr}, f_hess[2] = {nullptr, nullptr},
-               f_adapt[3] = {nullptr, nullptr, nullptr};
+               f_adapt[3] = {nullptr, nullptr, nullptr},  // [0] unused, [1] adapt_grad, [2] suffix
+               f_adaptk[2] = {nullptr, nullptr};
   static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st,
                         bool pdl = false) {
     RtApi& R = rt_api();
@@ -495,7 +496,7 @@ struct MpxRtPhase final : MpxPhaseKernels {
     return e != cudaSuccess || a.ticket ? e : go(f_hess[1], a, 1, MPX_HESS_FINAL_THREADS, 0, st);
   }
   cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
-    return go(f_adapt[0], a, grid, MPX_THREADS, smem, st);
+    return go(f_adaptk[a.ad_jac ? 1 : 0], a, grid, MPX_THREADS, smem, st);
   }
   cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const override {
     cudaError_t e = go(f_adapt[1], a, grid, MPX_THREADS, 0, st);
@@ -538,13 +539,13 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   std::vector<std::string> names;
   for (int ph = 0; ph < n_phases; ++ph)
     for (const char* k : {"mpx_gjac_kernel", "mpx_gjac2_kernel", "mpx_gjac4_kernel", "mpx_fgrad_kernel", "mpx_fgrad_final",
-                          "mpx_residual_kernel"})
+                          "mpx_residual_kernel", "mpx_adapt_kernel"})
       for (const char* b : {"false", "true"})
         names.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ", " + b +
                         (strcmp(k, "mpx_gjac4_kernel") == 0 || strcmp(k, "mpx_gjac2_kernel") == 0 ? ", 0>" : ">"));
   std::vector<std::string> names1;  // kernels with the phase functor as their only template argument
   for (int ph = 0; ph < n_phases; ++ph)
-    for (const char* k : {"mpx_hess_kernel", "mpx_hess_final", "mpx_adapt_kernel", "mpx_adapt_grad_kernel", "mpx_adapt_grad_suffix"})
+    for (const char* k : {"mpx_hess_kernel", "mpx_hess_final", "mpx_adapt_grad_kernel", "mpx_adapt_grad_suffix"})
       names1.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ">");
   for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
   for (auto& nm : names1) R.AddNameExpression(prog, nm.c_str());
@@ -573,8 +574,8 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   size_t idx = 0;
   for (int ph = 0; ph < n_phases; ++ph) {
     std::unique_ptr<MpxRtPhase> P(new MpxRtPhase());
-    CUfunction_t* slots[6] = {P->f_gjac, P->f_gjac2, P->f_gjac4, P->f_fgrad, P->f_final, P->f_resid};
-    for (int k = 0; k < 6; ++k)
+    CUfunction_t* slots[7] = {P->f_gjac, P->f_gjac2, P->f_gjac4, P->f_fgrad, P->f_final, P->f_resid, P->f_adaptk};
+    for (int k = 0; k < 7; ++k)
       for (int b = 0; b < 2; ++b, ++idx) {
         const char* lowered = nullptr;
         if (R.GetLoweredName(prog, names[idx].c_str(), &lowered) != 0 || !lowered ||
@@ -583,10 +584,10 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
           return fail(MPX_ECUDA, "kernel " + names[idx] + " not found in the run-time compiled module");
         }
       }
-    for (int b = 0; b < 5; ++b) {
+    for (int b = 0; b < 4; ++b) {
       const char* lowered = nullptr;
-      const std::string& nm = names1[(size_t)ph * 5 + b];
-      CUfunction_t* slot = b < 2 ? &P->f_hess[b] : &P->f_adapt[b - 2];
+      const std::string& nm = names1[(size_t)ph * 4 + b];
+      CUfunction_t* slot = b < 2 ? &P->f_hess[b] : &P->f_adapt[b - 1];
       if (R.GetLoweredName(prog, nm.c_str(), &lowered) != 0 || !lowered || R.ModuleGetFunction(slot, mod, lowered) != 0) {
         R.DestroyProgram(&prog);
         return fail(MPX_ECUDA, "kernel " + nm + " not found in the run-time compiled module");

@@ -153,10 +153,15 @@ struct MpxAotPhase final : MpxPhaseKernels {
     return cudaGetLastError();
   }
   cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
-    static bool done = false;
-    cudaError_t e = allow_smem(mpx_adapt_kernel<PH>, smem, done);
-    if (e != cudaSuccess) return e;
-    mpx_adapt_kernel<PH><<<grid, MPX_THREADS, smem, st>>>(a);
+    static bool d0 = false, d1 = false;
+    cudaError_t e;
+    if (a.ad_jac) {
+      if ((e = allow_smem(mpx_adapt_kernel<PH, true>, smem, d1)) != cudaSuccess) return e;
+      mpx_adapt_kernel<PH, true><<<grid, MPX_THREADS, smem, st>>>(a);
+    } else {  // g only: a separate instance, so that the row-assembly code does not set its register count
+      if ((e = allow_smem(mpx_adapt_kernel<PH, false>, smem, d0)) != cudaSuccess) return e;
+      mpx_adapt_kernel<PH, false><<<grid, MPX_THREADS, smem, st>>>(a);
+    }
     return cudaGetLastError();
   }
   cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const override {
