@@ -281,6 +281,13 @@ class post_process:
         self.solution, self.mpo, self.scaling = solution, mpo, scaling
         self.phases = list(range(mpo._ocp.n_phases))
 
+    def __getattr__(self, name):
+        # plot_phases / plot_x / plot_u / plot_residuals ... (mpopt.py:1838-2270) need matplotlib: out of scope, say so
+        if name.startswith("plot"):
+            raise NotImplementedError(f"post_process.{name}: plotting (matplotlib) is outside the accelerated path; "
+                                      "use get_data() / get_data(interpolate=True) and plot the arrays")
+        raise AttributeError(name)
+
     def get_trajectories(self, phase: int = 0):
         """(x, u, t, a) of one phase, unscaled unless ``scaling`` (mpopt.py:1639-1667)."""
         mpo = self.mpo

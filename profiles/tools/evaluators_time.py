@@ -51,3 +51,19 @@ for name, (fn, nbytes) in calls.items():
     us = e0.elapsed_time(e1) * 10
     print(json.dumps({"evaluator": name, "us": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2), "GBs": round(nbytes / us / 1e3, 1)}))
 print(json.dumps({"nnz_jac": tr.nnz, "nnz_hess_lower": nh}))
+
+# the inner step of every h-adaptive pass: dynamics residual at the mid points of all segments (host-pointer entry
+# point: upload of z, kernel, download of six arrays), wall clock
+import time
+
+zh = z.copy()
+ph = rng.dirichlet(np.ones(4096))
+taus = [0.5 * (tr.tables(15)[0][:-1] + tr.tables(15)[0][1:])] * 4096
+for _ in range(3):
+    out = tr.residuals(zh, ph, 0, taus)
+t0 = time.perf_counter()
+for _ in range(20):
+    out = tr.residuals(zh, ph, 0, taus)
+ms = (time.perf_counter() - t0) / 20 * 1e3
+print(json.dumps({"evaluator": "dynamics residuals at 61 440 mid points (mpx_eval_residuals, host pointers, wall clock)",
+                  "ms": round(ms, 3), "points": int(sum(out["counts"]))}))
