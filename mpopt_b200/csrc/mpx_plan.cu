@@ -219,6 +219,7 @@ struct mpx_plan {
   std::vector<double> h_dmid;              // D at the mid points, [d][d+1] per degree
   DevBuf d_dmid, d_seg_dmid, d_wpart, d_seg_rpre;  // d_seg_rpre: [P][K]
   DevBuf d_ticket;                                 // [P] arrival counters of the single-launch f + grad_f kernel
+  DevBuf d_rseg, d_rtau, d_rout;                   // mpx_eval_residuals: point list and outputs
   int smem_adapt = 0;
   std::vector<int> adapt_img;              // per phase: doubles of a staged residual-row image (0: direct stores)
   std::vector<int64_t> sw_direct;          // per phase: CSR position of the SW block when it is written in place, else -1
@@ -1989,7 +1990,7 @@ extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw
   if (rc || n_points == 0) return rc;
   const int nx = p->nx, nu = p->nu;
   const bool deriv = dxi || dui || res;
-  DevBuf dseg, dtau, dout;
+  DevBuf &dseg = p->d_rseg, &dtau = p->d_rtau, &dout = p->d_rout;  // plan-owned, grow-only: the h-adaptive loop calls this every pass
   const size_t per = (size_t)(2 * nx + 2 * nu + 1 + nx);
   CUDA_TRY(dseg.ensure((size_t)n_points * sizeof(int32_t)));
   CUDA_TRY(dtau.ensure((size_t)n_points * sizeof(double)));

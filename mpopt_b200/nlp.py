@@ -213,11 +213,11 @@ class Transcription:
         z, p = self._zp(z, p)
         if taus is None or len(taus) != self.K:
             raise ValueError("taus must hold one array per segment")
-        counts = [len(t) for t in taus]
-        n = int(sum(counts))
+        counts = np.fromiter(map(len, taus), dtype=np.int64, count=self.K)
+        n = int(counts.sum())
         seg = np.repeat(np.arange(self.K, dtype=np.int32), counts)
-        tau = np.ascontiguousarray(np.concatenate([np.asarray(t, dtype=float).reshape(-1) for t in taus])
-                                   if n else np.zeros(0))
+        tau = np.ascontiguousarray(np.concatenate(taus), dtype=float).reshape(-1) if n else np.zeros(0)
+        counts = counts.tolist()
         out = {"xi": np.empty((n, self.nx)), "ui": np.empty((n, self.nu)), "ti": np.empty(n), "counts": counts}
         if derivatives:
             out.update(dxi=np.empty((n, self.nx)), dui=np.empty((n, self.nu)), res=np.empty((n, self.nx)))
