@@ -184,6 +184,11 @@ int mpx_eval_hess_l_dev(mpx_plan* plan, const double* d_z, const double* d_p, do
 int mpx_eval_residuals(mpx_plan* plan, const double* z, const double* p, int32_t phase, int64_t n_points,
                        const int32_t* seg, const double* taus, double* xi, double* ui, double* ti, double* dxi,
                        double* dui, double* res);
+/* -- second derivatives of the interpolants at arbitrary points: replaces mpopt.get_state_second_derivative_single_phase
+ *    (mpopt.py:1285-1358; composite get_diff_matrix(order=2) times X and U). Same point list as above; ddxi[n][nx],
+ *    ddui[n][nu] are d2/dtau2 through the segment's Lagrange basis (either may be NULL, not both), ti[n] may be NULL. */
+int mpx_eval_second_derivatives(mpx_plan* plan, const double* z, const double* p, int32_t phase, int64_t n_points,
+                                const int32_t* seg, const double* taus, double* ti, double* ddxi, double* ddui);
 
 /* -- staged evaluation: ONE upload and ONE fused evaluation per distinct x, results kept in the plan's device
  *    buffers; the pieces are copied out when asked for. This is how the solver-facing shims below honour IPOPT's

@@ -1977,9 +1977,9 @@ extern "C" int mpx_eval_hess_l(mpx_plan* p, const double* z, const double* pw, d
 }
 
 // ------------------------------------------------------------------ interpolation / dynamics residual at arbitrary points
-extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw, int32_t phase, int64_t n_points,
-                                  const int32_t* seg, const double* taus, double* xi, double* ui, double* ti, double* dxi,
-                                  double* dui, double* res) {
+static int eval_points(mpx_plan* p, const double* z, const double* pw, int32_t phase, int64_t n_points, const int32_t* seg,
+                       const double* taus, double* xi, double* ui, double* ti, double* dxi, double* dui, double* res,
+                       double* ddxi, double* ddui) {
   if (!p) return fail(MPX_EINVAL, "NULL plan");
   if (phase < 0 || phase >= p->P) return fail(MPX_EINVAL, "phase out of range");
   if (n_points < 0 || (n_points && (!seg || !taus))) return fail(MPX_EINVAL, "bad point list");
@@ -1989,9 +1989,9 @@ extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw
   int rc = upload_inputs(*p, z, pw);
   if (rc || n_points == 0) return rc;
   const int nx = p->nx, nu = p->nu;
-  const bool deriv = dxi || dui || res;
+  const bool deriv = dxi || dui || res || ddxi || ddui;
   DevBuf &dseg = p->d_rseg, &dtau = p->d_rtau, &dout = p->d_rout;  // plan-owned, grow-only: the h-adaptive loop calls this every pass
-  const size_t per = (size_t)(2 * nx + 2 * nu + 1 + nx);
+  const size_t per = (size_t)(2 * nx + 2 * nu + 1 + nx) + (size_t)(nx + nu);
   CUDA_TRY(dseg.ensure((size_t)n_points * sizeof(int32_t)));
   CUDA_TRY(dtau.ensure((size_t)n_points * sizeof(double)));
   CUDA_TRY(dout.ensure((size_t)n_points * per * sizeof(double)));
@@ -2008,7 +2008,9 @@ extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw
   a.r_ti = o, o += n_points;
   a.r_dxi = o, o += n_points * nx;
   a.r_dui = o, o += n_points * nu;
-  a.r_res = o;
+  a.r_res = o, o += n_points * nx;
+  a.r_ddxi = ddxi ? o : nullptr, o += n_points * nx;
+  a.r_ddui = ddui ? o : nullptr;
   CUDA_TRY(p->prog->phases[phase]->residual(a, deriv, (int)((n_points + 127) / 128), p->stream));
   ++p->launches;
   auto back = [&](double* dst, const double* src, size_t n) -> cudaError_t {
@@ -2020,8 +2022,22 @@ extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw
   CUDA_TRY(back(dxi, a.r_dxi, (size_t)n_points * nx));
   CUDA_TRY(back(dui, a.r_dui, (size_t)n_points * nu));
   CUDA_TRY(back(res, a.r_res, (size_t)n_points * nx));
+  if (ddxi) CUDA_TRY(back(ddxi, a.r_ddxi, (size_t)n_points * nx));
+  if (ddui) CUDA_TRY(back(ddui, a.r_ddui, (size_t)n_points * nu));
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;
+}
+
+extern "C" int mpx_eval_residuals(mpx_plan* p, const double* z, const double* pw, int32_t phase, int64_t n_points,
+                                  const int32_t* seg, const double* taus, double* xi, double* ui, double* ti, double* dxi,
+                                  double* dui, double* res) {
+  return eval_points(p, z, pw, phase, n_points, seg, taus, xi, ui, ti, dxi, dui, res, nullptr, nullptr);
+}
+
+extern "C" int mpx_eval_second_derivatives(mpx_plan* p, const double* z, const double* pw, int32_t phase, int64_t n_points,
+                                           const int32_t* seg, const double* taus, double* ti, double* ddxi, double* ddui) {
+  if (!ddxi && !ddui) return fail(MPX_EINVAL, "ddxi and ddui are both NULL");
+  return eval_points(p, z, pw, phase, n_points, seg, taus, nullptr, nullptr, ti, nullptr, nullptr, nullptr, ddxi, ddui);
 }
 
 // ------------------------------------------------------------------ staged evaluation (one upload, one fused

@@ -266,6 +266,34 @@ class mpopt:
                 residuals[phase] = [r / mx if r is not None else None for r in residuals[phase]]
         return ti, residuals
 
+    def get_state_second_derivative_single_phase(self, solution, phase: int = 0, nodes=None, grid_type: str = None,
+                                                 residual_type: str = None):
+        """(ti, ddx, ddu) per segment: second tau-derivative of the state / control interpolants at the given local
+        taus, evaluated on the GPU (mpopt.py:1285-1358); None for a segment without points."""
+        target = nodes if nodes is not None else self.get_residual_grid_taus(phase=phase, grid_type=self.grid_type[phase])
+        z = np.asarray(solution["x"], dtype=float).reshape(-1)
+        r = self.transcription.second_derivatives(z, self._current_widths(), phase, target)
+        off = np.concatenate([[0], np.cumsum(r["counts"])]).astype(int)
+        K = self.n_segments
+        ti, ddx, ddu = [None] * K, [None] * K, [None] * K
+        for k in range(K):
+            if off[k] == off[k + 1]:
+                continue
+            ddx[k], ddu[k] = r["ddxi"][off[k]: off[k + 1]], r["ddui"][off[k]: off[k + 1]]
+            if residual_type == "relative":
+                ddx[k], ddu[k] = ddx[k] / ddx[k].max(), ddu[k] / ddu[k].max()
+            ti[k] = r["ti"][off[k]: off[k + 1]]
+        return ti, ddx, ddu
+
+    def get_state_second_derivative(self, solution, grid_type="spectral", nodes=None, plot=False, fig=None, axs=None):
+        """mpopt.py:1238-1283: the above for every phase."""
+        P = self._ocp.n_phases
+        ti, DDx, DDu = [None] * P, [None] * P, [None] * P
+        for phase in range(P):
+            target = nodes[phase] if nodes is not None else self.get_residual_grid_taus(phase, grid_type=grid_type)
+            ti[phase], DDx[phase], DDu[phase] = self.get_state_second_derivative_single_phase(solution, phase, nodes=target)
+        return ti, DDx, DDu
+
     # ------------------------------------------------------------------ results
     def process_results(self, solution, plot: bool = False, scaling: bool = False, residual_x=False, residual_dx=False):
         return post_process(solution, self, scaling)

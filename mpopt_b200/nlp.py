@@ -227,6 +227,24 @@ class Transcription:
                                               ptr("dxi"), ptr("dui"), ptr("res")))
         return out
 
+    def second_derivatives(self, z, p=None, phase=0, taus=None):
+        """d2/dtau2 of the state / control interpolants at per-segment local abscissae (mpopt.py:1285-1358: composite
+        ``get_diff_matrix(order=2)`` times X, U).  Returns ``ti`` (n,), ``ddxi`` (n, nx), ``ddui`` (n, nu), ``counts``."""
+        z, p = self._zp(z, p)
+        if taus is None or len(taus) != self.K:
+            raise ValueError("taus must hold one array per segment")
+        counts = np.fromiter(map(len, taus), dtype=np.int64, count=self.K)
+        n = int(counts.sum())
+        seg = np.repeat(np.arange(self.K, dtype=np.int32), counts)
+        tau = np.ascontiguousarray(np.concatenate(taus), dtype=float).reshape(-1) if n else np.zeros(0)
+        out = {"ti": np.empty(n), "ddxi": np.empty((n, self.nx)), "ddui": np.empty((n, self.nu)), "counts": counts.tolist()}
+        if n:
+            _lib.check(self._L.mpx_eval_second_derivatives(self._plan, _lib.ptr(z), _lib.ptr(p), int(phase), n,
+                                                           _lib.ptr(seg, _lib.c_i32p), _lib.ptr(tau), _lib.ptr(out["ti"]),
+                                                           _lib.ptr(out["ddxi"]) if self.nx else None,
+                                                           _lib.ptr(out["ddui"]) if self.nu else None))
+        return out
+
     # ------------------------------------------------------------------ evaluators (device pointers)
     def g_jac_dev(self, z_ptr, p_ptr, g_ptr, vals_ptr, stream=None):
         _lib.check(self._L.mpx_eval_g_jac_dev(self._plan, z_ptr, p_ptr, g_ptr, vals_ptr, stream))

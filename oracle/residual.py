@@ -75,6 +75,16 @@ def interpolate_phase(ora, z, p, phase, taus):
     return CI @ X, CI @ U, ti, DI @ X, DI @ U
 
 
+def second_derivatives_phase(ora, z, p, phase, taus):
+    """mpopt.py:1285-1358: (ti, DDXi, DDUi) -- the composite second-order differentiation matrix at the local taus
+    (get_composite_interpolation_Dmatrix_at(..., order=2)) applied to X and U."""
+    X, U, T0, TF, A = ora._unpack(phase, np.asarray(z, dtype=float))
+    p = ora.seg_width_params() if p is None else np.asarray(p, dtype=float)
+    _, t, _, _ = ora._time_grid(phase, T0, TF, ora._widths(phase, z, p)[0])
+    D2 = ora.tab.composite_interpolation(taus, 2)
+    return interpolated_time_grid(t, taus, ora.po, ora.tau0, ora.tau1), D2 @ X, D2 @ U
+
+
 def dynamics_residuals_phase(ora, z, p, phase, taus):
     """mpopt.py:1428-1487: residual = D_I X - h_seg * Sx f(Xi / Sx, Ui / Su, ti, a / Sa) at every point.
     Returns (ti, residual, F) as flat (n_points, nx) arrays plus the list of per-segment point counts."""

@@ -166,3 +166,21 @@ def test_trust_constr_with_exact_hessian(mp):
     sol2 = mpo2.solve(nlp_solver_options={"method": "trust-constr", "max_iter": 300, "tol": 1e-8,
                                           "hessian_approximation": "limited-memory"})
     assert it_exact <= mpo2.nlp_solver.stats["iter_count"], (it_exact, mpo2.nlp_solver.stats)
+
+
+def test_state_second_derivative(mp):
+    """tests/test_mpopt.py:1136-1158: on the Chachuat solution x = -2 t^2 + 6 t + 1, u = 2 (t - 1) (tau in [0, 1], tf = 1)
+    the second derivative of the state interpolant is -4 and that of the control 0."""
+    from mpopt_b200.problems import chachuat_3_10
+
+    mp.CollocationRoots._TAU_MIN = 0
+    try:
+        mpo = mp.mpopt(chachuat_3_10(), 1, 5)
+        sol = mpo.solve(nlp_solver_options={"tol": 1e-14})
+        taus = [mpo.collocation._taus_fn(deg)[1:-1] for deg in mpo.poly_orders]
+        time, ddx, ddu = mpo.get_state_second_derivative_single_phase(sol, nodes=taus)
+        assert all((abs(d + 4) < 1e-3).all() for d in ddx) and all((abs(d) < 1e-3).all() for d in ddu)
+        ti, DDx, DDu = mpo.get_state_second_derivative(sol, nodes=[taus])
+        assert len(DDx) == 1 and np.allclose(DDx[0][0], ddx[0])
+    finally:
+        mp.CollocationRoots._TAU_MIN = -1

@@ -414,3 +414,27 @@ def test_lagrangian_hessian_matches_oracle(libmpx, problem, K, po, scheme):
     # a second point and other multipliers through the same plan (positions are reused, nothing stale is left behind)
     z2, lam2 = z + 1e-2, rng.uniform(-2, 2, ora.n_g)
     assert_close(tr.hess_l_values(z2, p, 1.0, lam2), hess_l(ora, z2, p, 1.0, lam2).data, "hess_l values, second point")
+
+
+@pytest.mark.parametrize("problem,K,po,scheme", [("van_der_pol", 5, [3, 6, 4, 9, 2], "LGR"), ("kitchen_sink", 3, [5, 7, 4], "LGL"),
+                                                 ("synthetic_6_3", 3, 15, "CGL")])
+def test_second_derivatives_match_oracle(libmpx, problem, K, po, scheme):
+    """mpx_eval_second_derivatives against the oracle's composite D2 (mpopt.py:1285-1358), points on and off the nodes."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle import residual as R
+    from oracle.nlp import OracleNLP
+
+    tr = Transcription(REGISTRY[problem](), K, po, scheme)
+    ora = OracleNLP(REGISTRY[problem](), K, po, scheme)
+    z, p = random_point(ora, dirichlet=True)
+    rng = np.random.default_rng(8)
+    taus = [np.sort(rng.uniform(-1, 1, int(rng.integers(0, 6)))) for _ in range(ora.K)]
+    taus[0] = np.array([-1.0, ora.tab.roots[ora.po[0]][1], 1.0])  # segment ends and a collocation node
+    for ph in range(ora.P):
+        ti, ddx, ddu = R.second_derivatives_phase(ora, z, p, ph, taus)
+        out = tr.second_derivatives(z, p, ph, taus)
+        assert out["counts"] == [len(t) for t in taus]
+        assert_close(out["ti"], ti, "ti")
+        scale = max(1.0, np.abs(ddx).max(), np.abs(ddu).max())
+        assert np.abs(out["ddxi"] - ddx).max() <= 1e-9 * scale and np.abs(out["ddui"] - ddu).max() <= 1e-9 * scale

@@ -60,3 +60,25 @@ def test_residual_vanishes_on_an_exact_polynomial_solution():
     assert n == [3, 0, 1, 2] and np.allclose(res, 0.0, atol=1e-11)
     tis, ress = R.dynamics_residuals(ora, z, p, nodes=[taus])
     assert ress[0][1] is None and ress[0][0].shape == (3, 1)
+
+
+def test_second_derivative_of_an_exact_polynomial_solution():
+    """mpopt.py:1285-1358 on x = t^2, u = 2 t over [0, 2] with unequal segments: d2x/dtau2 = 2 (dt/dtau)^2 = 2 (h_k / 1)^2
+    with dt/dtau = h_k = (tf - t0)/delta * w_k, and d2u/dtau2 = 0 -- the known answer the reference checks in the same way
+    for x = -2 t^2 + 6 t + 1 (tests/test_mpopt.py:1136-1158)."""
+    from mpopt_b200 import OCP
+
+    ocp = OCP(n_states=1, n_controls=1)
+    ocp.dynamics[0] = lambda x, u, t: [u[0]]
+    ocp.validate()
+    ora = OracleNLP(ocp, 3, [3, 2, 4], "LGR")
+    p = np.array([0.2, 0.5, 0.3])
+    z = np.zeros(ora.n_z)
+    z[ora.colT0(0)], z[ora.colTF(0)] = 0.0, 2.0
+    _, t, _, _ = ora._time_grid(0, 0.0, 2.0, p)
+    z[: ora.N], z[ora.N: 2 * ora.N] = t ** 2, 2 * t
+    taus = [np.array([-0.5, 0.25]), np.array([0.0]), np.array([-1.0, 0.3, 1.0])]
+    ti, ddx, ddu = R.second_derivatives_phase(ora, z, p, 0, taus)
+    h = (2.0 - 0.0) / 2.0 * np.repeat(p, [2, 1, 3])
+    assert np.allclose(ddx[:, 0], 2 * h ** 2, atol=1e-10) and np.allclose(ddu, 0.0, atol=1e-10)
+    assert ti.shape == (6,)
