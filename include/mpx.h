@@ -189,6 +189,14 @@ int mpx_eval_residuals(mpx_plan* plan, const double* z, const double* p, int32_t
  *    ddui[n][nu] are d2/dtau2 through the segment's Lagrange basis (either may be NULL, not both), ti[n] may be NULL. */
 int mpx_eval_second_derivatives(mpx_plan* plan, const double* z, const double* p, int32_t phase, int64_t n_points,
                                 const int32_t* seg, const double* taus, double* ti, double* ddxi, double* ddui);
+/* -- state residual by quadrature: replaces mpopt.compute_states_from_solution_dynamics / get_states_residuals
+ *    (mpopt.py:989-1150). Per segment, h Sx f evaluated at the segment's target points is interpolated through those
+ *    points and integrated from tau_min to every target point; xint[n][nx] = x(segment start) + integral (scaled
+ *    states), res_x[n][nx] = interpolated state - xint. Points must be listed segment by segment (as the reference's
+ *    per-segment tau lists are). ui[n][nu], ti[n] as in mpx_eval_residuals; any output may be NULL except that one of
+ *    xint / res_x is required. */
+int mpx_eval_state_residuals(mpx_plan* plan, const double* z, const double* p, int32_t phase, int64_t n_points,
+                             const int32_t* seg, const double* taus, double* xint, double* ui, double* ti, double* res_x);
 
 /* -- staged evaluation: ONE upload and ONE fused evaluation per distinct x, results kept in the plan's device
  *    buffers; the pieces are copied out when asked for. This is how the solver-facing shims below honour IPOPT's

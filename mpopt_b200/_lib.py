@@ -86,6 +86,8 @@ PROTOTYPES = {
                                      c_f64p, c_f64p, c_f64p, c_f64p]),
     "mpx_eval_second_derivatives": (C.c_int, [C.c_void_p, c_f64p, c_f64p, C.c_int32, C.c_int64, c_i32p, c_f64p, c_f64p,
                                               c_f64p, c_f64p]),
+    "mpx_eval_state_residuals": (C.c_int, [C.c_void_p, c_f64p, c_f64p, C.c_int32, C.c_int64, c_i32p, c_f64p, c_f64p,
+                                           c_f64p, c_f64p, c_f64p]),
     "mpx_stage": (C.c_int, [C.c_void_p, c_f64p, c_f64p, C.c_int32]),
     "mpx_staged": (C.c_int, [C.c_void_p]),
     "mpx_fetch": (C.c_int, [C.c_void_p, C.c_int32, c_f64p]),

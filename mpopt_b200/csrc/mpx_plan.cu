@@ -122,6 +122,68 @@ __global__ void mpx_compact_kernel(const double* __restrict__ full, const int64_
   if (i < n) out[i] = full[map[i]];
 }
 
+// state residual by quadrature (mpopt.compute_states_from_solution_dynamics, mpopt.py:989-1076): per segment, the
+// Lagrange interpolant of F = h Sx f through the segment's own target points is integrated from tau0 to every target
+// point (Gauss-Legendre, exact for the interpolant), x_int = x(segment start) + integral, residual = x_I - x_int.
+// F comes from the residual kernel (dxi - res).  One CTA per segment, one thread per target point.
+struct MpxSrArgs {
+  const double* z;          // phase slice of the decision vector (state-major)
+  const int32_t* seg_start; // [K+1]
+  const int32_t* pt_off;    // [K+1] first point of every segment
+  const double* tau;        // [n] local abscissae
+  const double* xi;         // [n][nx] interpolated states
+  const double* dxi;        // [n][nx]
+  const double* res;        // [n][nx] dynamics residual (dxi - h Sx f)
+  double* xint;             // [n][nx] out
+  double* rx;               // [n][nx] out
+  int32_t N, nx, max_pts;
+  double tau0;
+};
+#define MPX_SR_THREADS 64
+__global__ void __launch_bounds__(MPX_SR_THREADS) mpx_state_resid_kernel(const MpxSrArgs A) {
+  extern __shared__ __align__(16) double sm[];
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const int p0 = A.pt_off[k], nt = A.pt_off[k + 1] - p0;
+  if (nt == 0) return;
+  const int nx = A.nx, nq = nt / 2 + 1;
+  double* sT = sm;                    // target abscissae (the custom roots)
+  double* sB = sT + A.max_pts;        // 1 / prod_{i != m} (r_m - r_i)
+  double* sF = sB + A.max_pts;        // F[m][s]
+  double* xq = sF + A.max_pts * nx;
+  double* wq = xq + A.max_pts;
+  for (int i = tid; i < nt; i += MPX_SR_THREADS) sT[i] = A.tau[p0 + i];
+  for (int i = tid; i < nt * nx; i += MPX_SR_THREADS) sF[i] = A.dxi[(int64_t)p0 * nx + i] - A.res[(int64_t)p0 * nx + i];
+  __syncthreads();
+  for (int m = tid; m < nt; m += MPX_SR_THREADS) {
+    double b = 1.0;
+    for (int i = 0; i < nt; ++i)
+      if (i != m) b *= sT[m] - sT[i];
+    sB[m] = 1.0 / b;
+  }
+  mpx_gauss_legendre(nq, xq, wq);  // ends with a barrier
+  for (int i = tid; i < nt; i += MPX_SR_THREADS) {
+    const double ta = A.tau0, tb = sT[i], half = 0.5 * (tb - ta);
+    double acc[MPX_MAXS];
+    for (int s = 0; s < nx; ++s) acc[s] = 0.0;
+    for (int q = 0; q < nq; ++q) {
+      const double xi_q = ta + half * (xq[q] + 1.0);
+      for (int m = 0; m < nt; ++m) {
+        double l = sB[m];
+        for (int j = 0; j < nt; ++j)
+          if (j != m) l *= xi_q - sT[j];
+        l *= wq[q];
+        for (int s = 0; s < nx; ++s) acc[s] = fma(l, sF[m * nx + s], acc[s]);
+      }
+    }
+    for (int s = 0; s < nx; ++s) {
+      const double xstart = A.z[(int64_t)s * A.N + A.seg_start[k]];
+      const double v = xstart + half * acc[s];
+      A.xint[(int64_t)(p0 + i) * nx + s] = v;
+      A.rx[(int64_t)(p0 + i) * nx + s] = A.xi[(int64_t)(p0 + i) * nx + s] - v;
+    }
+  }
+}
+
 // exclusive prefix sum of the segment widths of every phase (time grid, mpopt.py:192)
 #define MPX_SCAN_THREADS 1024
 __global__ void __launch_bounds__(MPX_SCAN_THREADS) mpx_scan_widths_kernel(const double* w, double* sig0, int K,
@@ -220,6 +282,7 @@ struct mpx_plan {
   DevBuf d_dmid, d_seg_dmid, d_wpart, d_seg_rpre;  // d_seg_rpre: [P][K]
   DevBuf d_ticket;                                 // [P] arrival counters of the single-launch f + grad_f kernel
   DevBuf d_rseg, d_rtau, d_rout;                   // mpx_eval_residuals: point list and outputs
+  DevBuf d_sr_off, d_sr_out;                       // mpx_eval_state_residuals: point offsets per segment, outputs
   int smem_adapt = 0;
   std::vector<int> adapt_img;              // per phase: doubles of a staged residual-row image (0: direct stores)
   std::vector<int64_t> sw_direct;          // per phase: CSR position of the SW block when it is written in place, else -1
@@ -1979,7 +2042,7 @@ extern "C" int mpx_eval_hess_l(mpx_plan* p, const double* z, const double* pw, d
 // ------------------------------------------------------------------ interpolation / dynamics residual at arbitrary points
 static int eval_points(mpx_plan* p, const double* z, const double* pw, int32_t phase, int64_t n_points, const int32_t* seg,
                        const double* taus, double* xi, double* ui, double* ti, double* dxi, double* dui, double* res,
-                       double* ddxi, double* ddui) {
+                       double* ddxi, double* ddui, bool force_deriv = false) {
   if (!p) return fail(MPX_EINVAL, "NULL plan");
   if (phase < 0 || phase >= p->P) return fail(MPX_EINVAL, "phase out of range");
   if (n_points < 0 || (n_points && (!seg || !taus))) return fail(MPX_EINVAL, "bad point list");
@@ -1989,7 +2052,7 @@ static int eval_points(mpx_plan* p, const double* z, const double* pw, int32_t p
   int rc = upload_inputs(*p, z, pw);
   if (rc || n_points == 0) return rc;
   const int nx = p->nx, nu = p->nu;
-  const bool deriv = dxi || dui || res || ddxi || ddui;
+  const bool deriv = dxi || dui || res || ddxi || ddui || force_deriv;
   DevBuf &dseg = p->d_rseg, &dtau = p->d_rtau, &dout = p->d_rout;  // plan-owned, grow-only: the h-adaptive loop calls this every pass
   const size_t per = (size_t)(2 * nx + 2 * nu + 1 + nx) + (size_t)(nx + nu);
   CUDA_TRY(dseg.ensure((size_t)n_points * sizeof(int32_t)));
@@ -2038,6 +2101,44 @@ extern "C" int mpx_eval_second_derivatives(mpx_plan* p, const double* z, const d
                                            const int32_t* seg, const double* taus, double* ti, double* ddxi, double* ddui) {
   if (!ddxi && !ddui) return fail(MPX_EINVAL, "ddxi and ddui are both NULL");
   return eval_points(p, z, pw, phase, n_points, seg, taus, nullptr, nullptr, ti, nullptr, nullptr, nullptr, ddxi, ddui);
+}
+
+extern "C" int mpx_eval_state_residuals(mpx_plan* p, const double* z, const double* pw, int32_t phase, int64_t n_points,
+                                        const int32_t* seg, const double* taus, double* xint, double* ui, double* ti,
+                                        double* res_x) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  if (!xint && !res_x) return fail(MPX_EINVAL, "xint and res_x are both NULL");
+  for (int64_t i = 1; i < n_points; ++i)
+    if (seg && seg[i] < seg[i - 1]) return fail(MPX_EINVAL, "points must be listed segment by segment");
+  // interpolation + dynamics residual of every point stay on the device (same buffer layout as eval_points)
+  int rc = eval_points(p, z, pw, phase, n_points, seg, taus, nullptr, ui, ti, nullptr, nullptr, nullptr, nullptr, nullptr, true);
+  if (rc || n_points == 0) return rc;
+  const int nx = p->nx, nu = p->nu, K = p->K;
+  std::vector<int32_t> off((size_t)K + 1, 0);
+  for (int64_t i = 0; i < n_points; ++i) ++off[(size_t)seg[i] + 1];
+  int max_pts = 0;
+  for (int k = 0; k < K; ++k) max_pts = std::max(max_pts, off[k + 1]), off[k + 1] += off[k];
+  CUDA_TRY(p->d_sr_off.ensure(off.size() * sizeof(int32_t)));
+  CUDA_TRY(p->d_sr_out.ensure((size_t)2 * n_points * nx * sizeof(double)));
+  CUDA_TRY(cudaMemcpyAsync(p->d_sr_off.p, off.data(), off.size() * sizeof(int32_t), cudaMemcpyHostToDevice, p->stream));
+  const double* o = p->d_rout.as<double>();
+  MpxSrArgs a;
+  a.z = p->d_z.as<double>() + p->ph[phase].zoff, a.seg_start = p->d_seg_start.as<int32_t>();
+  a.pt_off = p->d_sr_off.as<int32_t>(), a.tau = p->d_rtau.as<double>();
+  a.xi = o, a.dxi = o + n_points * (nx + nu + 1), a.res = a.dxi + n_points * (nx + nu);
+  a.xint = p->d_sr_out.as<double>(), a.rx = a.xint + n_points * nx;
+  a.N = p->N, a.nx = nx, a.max_pts = max_pts, a.tau0 = p->tau_min;
+  const size_t smem = (size_t)(4 * max_pts + max_pts * nx) * sizeof(double);
+  if (smem > 200 * 1024) return fail(MPX_ELIMIT, "too many target points in one segment for the state-residual kernel");
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(mpx_state_resid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mpx_state_resid_kernel<<<K, MPX_SR_THREADS, smem, p->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  ++p->launches;
+  if (xint) CUDA_TRY(cudaMemcpyAsync(xint, a.xint, (size_t)n_points * nx * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  if (res_x) CUDA_TRY(cudaMemcpyAsync(res_x, a.rx, (size_t)n_points * nx * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
 }
 
 // ------------------------------------------------------------------ staged evaluation (one upload, one fused

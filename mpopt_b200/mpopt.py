@@ -266,6 +266,39 @@ class mpopt:
                 residuals[phase] = [r / mx if r is not None else None for r in residuals[phase]]
         return ti, residuals
 
+    def compute_states_from_solution_dynamics(self, solution, phase: int = 0, nodes=None):
+        """(xint, u, ti, residual) per segment: the states re-integrated from the dynamics at the target points by
+        quadrature, and their difference to the interpolated states, evaluated on the GPU (mpopt.py:989-1076)."""
+        target = nodes if nodes is not None else self.get_residual_grid_taus(phase=phase, grid_type=self.grid_type[phase])
+        z = np.asarray(solution["x"], dtype=float).reshape(-1)
+        r = self.transcription.state_residuals(z, self._current_widths(), phase, target)
+        off = np.concatenate([[0], np.cumsum(r["counts"])]).astype(int)
+        K = self.n_segments
+        xint, uu, ti, res = [None] * K, [None] * K, [None] * K, [None] * K
+        for k in range(K):
+            if off[k] == off[k + 1]:
+                continue
+            sl = slice(off[k], off[k + 1])
+            xint[k], uu[k], ti[k], res[k] = r["xint"][sl], r["ui"][sl], r["ti"][sl], list(r["res_x"][sl])
+        return xint, uu, ti, res
+
+    def get_states_residuals(self, solution, phases=None, nodes=None, residual_type=None, plot=False, fig=None, axs=None):
+        """mpopt.py:1078-1150: the above for the given phases; ``residual_type="relative"`` divides by the largest
+        |xint| per state."""
+        P = self._ocp.n_phases
+        x_int, u_int, residuals, ti = [None] * P, [None] * P, [None] * P, [None] * P
+        for phase in (range(P) if phases is None else phases):
+            target = nodes[phase] if nodes is not None else self.get_residual_grid_taus(phase, grid_type=self.grid_type[phase])
+            x_int[phase], u_int[phase], ti[phase], residuals[phase] = self.compute_states_from_solution_dynamics(
+                solution, phase, nodes=target)
+            if residual_type == "relative":
+                mx = np.zeros(self._ocp.nx)
+                for seg in x_int[phase]:
+                    if seg is not None:
+                        mx = np.maximum(mx, np.abs(np.asarray(seg)).max(axis=0))
+                residuals[phase] = [np.asarray(r_) / mx if r_ is not None else None for r_ in residuals[phase]]
+        return x_int, u_int, ti, residuals
+
     def get_state_second_derivative_single_phase(self, solution, phase: int = 0, nodes=None, grid_type: str = None,
                                                  residual_type: str = None):
         """(ti, ddx, ddu) per segment: second tau-derivative of the state / control interpolants at the given local

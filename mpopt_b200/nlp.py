@@ -227,6 +227,26 @@ class Transcription:
                                               ptr("dxi"), ptr("dui"), ptr("res")))
         return out
 
+    def state_residuals(self, z, p=None, phase=0, taus=None):
+        """State residual by quadrature at per-segment target points (mpopt.py:989-1076): ``xint`` = state at the
+        segment start + integral of the interpolated ``h Sx f`` up to each point, ``res_x = xi - xint``; also ``ui``,
+        ``ti``, ``counts``.  All arrays have one row per point, segment by segment."""
+        z, p = self._zp(z, p)
+        if taus is None or len(taus) != self.K:
+            raise ValueError("taus must hold one array per segment")
+        counts = np.fromiter(map(len, taus), dtype=np.int64, count=self.K)
+        n = int(counts.sum())
+        seg = np.repeat(np.arange(self.K, dtype=np.int32), counts)
+        tau = np.ascontiguousarray(np.concatenate(taus), dtype=float).reshape(-1) if n else np.zeros(0)
+        out = {"xint": np.empty((n, self.nx)), "res_x": np.empty((n, self.nx)), "ui": np.empty((n, self.nu)),
+               "ti": np.empty(n), "counts": counts.tolist()}
+        if n:
+            _lib.check(self._L.mpx_eval_state_residuals(self._plan, _lib.ptr(z), _lib.ptr(p), int(phase), n,
+                                                        _lib.ptr(seg, _lib.c_i32p), _lib.ptr(tau), _lib.ptr(out["xint"]),
+                                                        _lib.ptr(out["ui"]) if self.nu else None, _lib.ptr(out["ti"]),
+                                                        _lib.ptr(out["res_x"])))
+        return out
+
     def second_derivatives(self, z, p=None, phase=0, taus=None):
         """d2/dtau2 of the state / control interpolants at per-segment local abscissae (mpopt.py:1285-1358: composite
         ``get_diff_matrix(order=2)`` times X, U).  Returns ``ti`` (n,), ``ddxi`` (n, nx), ``ddui`` (n, nu), ``counts``."""

@@ -75,6 +75,30 @@ def interpolate_phase(ora, z, p, phase, taus):
     return CI @ X, CI @ U, ti, DI @ X, DI @ U
 
 
+def states_from_dynamics_phase(ora, z, p, phase, taus):
+    """mpopt.py:989-1076: per segment, Lagrange polynomials on the segment's own target points (:1025-1028), their
+    integrals from tau0 to every target point (:1056-1058), x_int = x(segment start) + h_seg * quad^T (f * scale_x)
+    (:1059-1061) and residual = x_I - x_int (:1062).  Returns flat (n_points, nx) arrays (xint, res_x) and ti."""
+    from .collocation import quadrature_weights
+
+    z = np.asarray(z, dtype=float)
+    X, U, T0, TF, A = ora._unpack(phase, z)
+    Xi, Ui, ti, DXi, _ = interpolate_phase(ora, z, p, phase, taus)
+    _, res, F, n = dynamics_residuals_phase(ora, z, p, phase, taus)  # F = h_seg * Sx f at the points
+    xint = np.zeros_like(Xi)
+    off = np.concatenate([[0], np.cumsum(n)]).astype(int)
+    for k in range(ora.K):
+        r = np.asarray(taus[k], dtype=float)
+        if len(r) == 0:
+            continue
+        xstart = X[ora.seg_start[k], :]
+        Fk = F[off[k]: off[k + 1]]
+        for i, tau in enumerate(r):
+            w = quadrature_weights(r, ora.tau0, tau)
+            xint[off[k] + i] = xstart + w @ Fk
+    return xint, Xi - xint, ti
+
+
 def second_derivatives_phase(ora, z, p, phase, taus):
     """mpopt.py:1285-1358: (ti, DDXi, DDUi) -- the composite second-order differentiation matrix at the local taus
     (get_composite_interpolation_Dmatrix_at(..., order=2)) applied to X and U."""

@@ -184,3 +184,23 @@ def test_state_second_derivative(mp):
         assert len(DDx) == 1 and np.allclose(DDx[0][0], ddx[0])
     finally:
         mp.CollocationRoots._TAU_MIN = -1
+
+
+def test_states_residuals_on_the_analytic_solution(mp):
+    """tests/test_mpopt.py:730-760 style bound: on the Chachuat solution the state re-integrated from the dynamics agrees
+    with the interpolated state (residual < 1e-3 everywhere), per phase / per segment lists like the reference's."""
+    from mpopt_b200.problems import chachuat_3_10
+
+    mp.CollocationRoots._TAU_MIN = 0
+    try:
+        mpo = mp.mpopt(chachuat_3_10(), 2, 4)
+        sol = mpo.solve(nlp_solver_options={"tol": 1e-14})
+        x_int, u_int, ti, res = mpo.get_states_residuals(sol)
+        assert len(res) == 1 and len(res[0]) == 2
+        for seg in res[0]:
+            assert seg is not None and (np.abs(np.asarray(seg)) < 1e-3).all()
+        t_all = np.concatenate(ti[0])
+        x_all = np.vstack(x_int[0])[:, 0]
+        assert (abs(x_all - (-2 * t_all ** 2 + 6 * t_all + 1)) < 1e-3).all()
+    finally:
+        mp.CollocationRoots._TAU_MIN = -1

@@ -438,3 +438,30 @@ def test_second_derivatives_match_oracle(libmpx, problem, K, po, scheme):
         assert_close(out["ti"], ti, "ti")
         scale = max(1.0, np.abs(ddx).max(), np.abs(ddu).max())
         assert np.abs(out["ddxi"] - ddx).max() <= 1e-9 * scale and np.abs(out["ddui"] - ddu).max() <= 1e-9 * scale
+
+
+@pytest.mark.parametrize("problem,K,po,scheme", [("van_der_pol", 5, [3, 6, 4, 9, 2], "LGR"), ("kitchen_sink", 3, [5, 7, 4], "LGL"),
+                                                 ("synthetic_6_3", 3, 15, "CGL"), ("two_phase_schwartz", 4, 5, "LGR")])
+def test_state_residuals_match_oracle(libmpx, problem, K, po, scheme):
+    """mpx_eval_state_residuals (mpopt.py:989-1076) against the oracle: segments with 0 .. 8 target points, the
+    reference's "spectral" grid, points on the segment ends."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle import residual as R
+    from oracle.nlp import OracleNLP
+
+    tr = Transcription(REGISTRY[problem](), K, po, scheme)
+    ora = OracleNLP(REGISTRY[problem](), K, po, scheme)
+    z, p = random_point(ora, dirichlet=True)
+    rng = np.random.default_rng(9)
+    custom = [np.sort(rng.uniform(-0.98, 1, int(rng.integers(0, 9)))) for _ in range(ora.K)]
+    custom[0] = np.array([-0.6, 0.1, 1.0])
+    for taus in (custom, R.residual_grid_taus(ora, 0, "spectral"), R.residual_grid_taus(ora, 0, "mid-points")):
+        for ph in range(ora.P):
+            xint, res, ti = R.states_from_dynamics_phase(ora, z, p, ph, taus)
+            out = tr.state_residuals(z, p, ph, taus)
+            assert out["counts"] == [len(t) for t in taus]
+            assert_close(out["ti"], ti, "ti")
+            assert_close(out["xint"], xint, "xint", 1e-9)
+            scale = max(1.0, np.abs(xint).max())
+            assert np.abs(out["res_x"] - res).max() <= 1e-9 * scale

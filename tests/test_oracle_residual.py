@@ -82,3 +82,29 @@ def test_second_derivative_of_an_exact_polynomial_solution():
     h = (2.0 - 0.0) / 2.0 * np.repeat(p, [2, 1, 3])
     assert np.allclose(ddx[:, 0], 2 * h ** 2, atol=1e-10) and np.allclose(ddu, 0.0, atol=1e-10)
     assert ti.shape == (6,)
+
+
+def test_state_residual_by_quadrature_known_answers():
+    """mpopt.py:989-1076.  (i) On an exact polynomial solution (x' = u, x = t^2) re-integrating the dynamics from the
+    segment start reproduces the interpolated state: residual 0.  (ii) With the control perturbed by a constant c the
+    re-integrated state drifts by c * (t - t_segment_start): the residual is minus that, a hand-checkable answer."""
+    from mpopt_b200 import OCP
+
+    ocp = OCP(n_states=1, n_controls=1)
+    ocp.dynamics[0] = lambda x, u, t: [u[0]]
+    ocp.validate()
+    ora = OracleNLP(ocp, 3, [3, 2, 4], "LGR")
+    p = np.array([0.2, 0.5, 0.3])
+    z = np.zeros(ora.n_z)
+    z[ora.colT0(0)], z[ora.colTF(0)] = 0.0, 2.0
+    _, t, _, _ = ora._time_grid(0, 0.0, 2.0, p)
+    z[: ora.N], z[ora.N: 2 * ora.N] = t ** 2, 2 * t
+    taus = [np.array([-0.5, 0.25, 0.8]), np.array([]), np.array([-0.9, 0.0, 0.3, 1.0])]
+    xint, res, ti = R.states_from_dynamics_phase(ora, z, p, 0, taus)
+    assert np.allclose(xint[:, 0], ti ** 2, atol=1e-12) and np.allclose(res, 0.0, atol=1e-12)
+    c = 0.37
+    z2 = z.copy()
+    z2[ora.N: 2 * ora.N] += c
+    xint2, res2, ti2 = R.states_from_dynamics_phase(ora, z2, p, 0, taus)
+    t_start = np.repeat(t[ora.seg_start], [3, 0, 4])
+    assert np.allclose(res2[:, 0], -c * (ti2 - t_start), atol=1e-12)
