@@ -421,6 +421,62 @@ def falcon9_launcher(drag=0.0, dyn_pressure=0.0, glide_slope=0.0):
     return ocp
 
 
+def alp_rider():
+    """Betts' alp rider (stiff 4-state system, a path constraint that depends on time through four Gaussian peaks);
+    restates examples/singlephase/Betts/alpr01_alp_rider.py:34-90, which tests/test_examples.py:38-50 solves."""
+    ocp = OCP(n_states=4, n_controls=2)
+    ocp.dynamics[0] = lambda x, u, t: [-10 * x[0] + u[0] + u[1], -2 * x[1] + u[0] + 2 * u[1],
+                                       -3 * x[2] + 5 * x[3] + u[0] - u[1], 5 * x[2] - 3 * x[3] + u[0] + 3 * u[1]]
+    ocp.terminal_constraints[0] = lambda xf, tf, x0, t0: [xf[0] - 2.0, xf[1] - 3.0, xf[2] - 1.0, xf[3] + 2]
+    ocp.running_costs[0] = lambda x, u, t: (100 * (x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3])
+                                            + 0.01 * (u[0] * u[0] + u[1] * u[1]))
+    peaks = ((3.0, 12, 3), (3.0, 10, 6), (3.0, 6, 10), (8.0, 4, 15))
+    ocp.path_constraints[0] = lambda x, u, t: [
+        sum(amp * ca.exp(-sharp * (t - at) * (t - at)) for amp, sharp, at in peaks) + 0.01
+        - x[0] * x[0] - x[1] * x[1] - x[2] * x[2] - x[3] * x[3]]
+    ocp.x00[0] = [2.0, 1.0, 2.0, 1.0]
+    ocp.xf0[0] = [2.0, 3.0, 1.0, -2.0]
+    ocp.tf0[0] = 20
+    ocp.lbtf[0] = ocp.ubtf[0] = 20.0
+    ocp.validate()
+    return ocp
+
+
+def mine_opt():
+    """Optimal ore extraction (the Wikipedia optimal-control example): cost u^2 / x - p u divides by the state;
+    restates examples/singlephase/mine_opt_wiki.py:30-52."""
+    ocp = OCP(n_states=1, n_controls=1)
+    ocp.dynamics[0] = lambda x, u, t: [-u[0]]
+    ocp.running_costs[0] = lambda x, u, t: u[0] * u[0] / x[0] - 1 * u[0]
+    ocp.x00[0] = [1.0]
+    ocp.lbx[0] = 0
+    ocp.ubx[0] = 1.0
+    ocp.lbtf[0] = ocp.ubtf[0] = 1.0
+    ocp.validate()
+    return ocp
+
+
+def dae_van_der_pol():
+    """Van der Pol with the state bound turned into a path constraint on a free parameter (n_params = 1, callables
+    with the 4-argument signature); restates examples/singlephase/dae_vdp.py:28-62."""
+    ocp = OCP(n_states=2, n_controls=1, n_params=1)
+    ocp.dynamics[0] = lambda x, u, t, a: [(1 - x[1] * x[1]) * x[0] - x[1] + u[0], x[0]]
+    ocp.running_costs[0] = lambda x, u, t, a: x[0] * x[0] + x[1] * x[1] + u[0] * u[0]
+    ocp.path_constraints[0] = lambda x, u, t, a: [a[0] - x[1]]
+    ocp.x00[0] = [0, 1]
+    ocp.lbu[0], ocp.ubu[0] = -1.0, 1.0
+    ocp.lba[0], ocp.uba[0] = 0.25, 0.5
+    ocp.lbx[0][1] = -0.25
+    ocp.lbtf[0] = ocp.ubtf[0] = 10.0
+    ocp.validate()
+    return ocp
+
+
+#: the reference's remaining example problems (tests/test_examples.py:38-50): not compiled ahead of time, so they
+#: exercise the run-time (NVRTC) route
+EXAMPLES = {"alp_rider": alp_rider, "mine_opt": mine_opt, "dae_van_der_pol": dae_van_der_pol}
+
+
 #: problems whose node functors are compiled ahead of time into libmpx.so by build()
 REGISTRY = {
     "moon_lander": moon_lander,

@@ -465,3 +465,35 @@ def test_state_residuals_match_oracle(libmpx, problem, K, po, scheme):
             assert_close(out["xint"], xint, "xint", 1e-9)
             scale = max(1.0, np.abs(xint).max())
             assert np.abs(out["res_x"] - res).max() <= 1e-9 * scale
+
+
+@pytest.mark.parametrize("name,K,po,scheme", [("alp_rider", 10, 5, "LGR"), ("mine_opt", 1, 30, "LGR"),
+                                              ("dae_van_der_pol", 50, 3, "LGR")])
+def test_reference_examples_run_time_compiled(libmpx, name, K, po, scheme):
+    """The remaining problems of the reference's tests/test_examples.py:38-50 at the sizes those modules build
+    (alpr01 10 x 5, mineopt 1 x 30, vdp 50 x 3): not registered, so their functors go through NVRTC; g, jac_g, f,
+    grad_f and hess_l against the oracle."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import EXAMPLES
+    from oracle.hessian import hess_l
+    from oracle.nlp import OracleNLP
+
+    tr = Transcription(EXAMPLES[name](), K, po, scheme, drop_exact_zeros=False)
+    ora = OracleNLP(EXAMPLES[name](), K, po, scheme, drop_exact_zeros=False)
+    assert tr.program_origin.startswith("nvrtc:")
+    z, p = random_point(ora, dirichlet=True)
+    if name == "mine_opt":
+        z = np.abs(z) + 0.5  # the cost divides by the state
+    J = ora.jac_g(z, p)
+    rp, ci = tr.structure()
+    assert np.array_equal(rp, J.indptr) and np.array_equal(ci, J.indices)
+    g = np.empty(tr.n_g)
+    assert_close(tr.jac_g_values(z, p, g_out=g), J.data, "jac_g values")
+    assert_close(g, ora.g(z, p), "g")
+    assert abs(tr.f(z, p) - ora.f(z, p)) <= 1e-10 * max(1.0, abs(ora.f(z, p)))
+    assert_close(tr.grad_f(z, p), ora.grad_f(z, p), "grad_f")
+    lam = np.random.default_rng(3).uniform(-1, 1, ora.n_g)
+    H = hess_l(ora, z, p, 0.7, lam)
+    hrp, hci = tr.hess_structure()
+    assert np.array_equal(hrp, H.indptr) and np.array_equal(hci, H.indices)
+    assert_close(tr.hess_l_values(z, p, 0.7, lam), H.data, "hess_l values")

@@ -131,3 +131,21 @@ def test_delta3_banner_bound_types_and_derivatives():
         assert np.abs(fd - J[:, j]).max() < 2e-6 * max(1.0, np.abs(J[:, j]).max()), j
         fdf = (n.f(z + e) - n.f(z - e)) / (2 * e[j])
         assert abs(fdf - gr[j]) < 2e-6 * max(1.0, abs(gr[j])), j
+
+
+@pytest.mark.parametrize("name,K,po", [("alp_rider", 3, [3, 4, 2]), ("mine_opt", 2, [4, 3]), ("dae_van_der_pol", 3, 3)])
+def test_reference_examples_jacobian_by_finite_differences(name, K, po):
+    """The remaining problems of tests/test_examples.py:38-50 (time-dependent path row, division by a state, a free
+    parameter in a path row)."""
+    n = OracleNLP(pr.EXAMPLES[name](), K, po, "LGR")
+    z, p = random_point(n, dirichlet=True)
+    z = np.abs(z) + 0.5 if name == "mine_opt" else z
+    J = n.jac_g(z, p).toarray()
+    gr = n.grad_f(z, p)
+    eps = 1e-6
+    for j in range(n.n_z):
+        e = np.zeros(n.n_z)
+        e[j] = eps
+        fd = (n.g(z + e, p) - n.g(z - e, p)) / (2 * eps)
+        assert np.abs(fd - J[:, j]).max() < 1e-6 * max(1.0, np.abs(J[:, j]).max()), j
+        assert abs((n.f(z + e, p) - n.f(z - e, p)) / (2 * eps) - gr[j]) < 1e-6 * max(1.0, abs(gr[j])), j

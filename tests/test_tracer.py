@@ -5,7 +5,9 @@ import pytest
 
 from helpers import eval_expr
 from mpopt_b200 import ca, trace as tr
-from mpopt_b200.problems import REGISTRY
+from mpopt_b200.problems import EXAMPLES, REGISTRY
+
+ALL_PROBLEMS = {**REGISTRY, **EXAMPLES}
 from mpopt_b200.program import Program
 from oracle.dual import Dual, Vec, flatten
 
@@ -37,9 +39,9 @@ def test_numpy_and_shim_interop():
         bool(x > 0) if hasattr(x, "__gt__") else bool(x)
 
 
-@pytest.mark.parametrize("name", sorted(REGISTRY))
+@pytest.mark.parametrize("name", sorted(ALL_PROBLEMS))
 def test_partials_and_pattern_match_oracle_duals(name):
-    ocp = REGISTRY[name]()
+    ocp = ALL_PROBLEMS[name]()
     prog = Program(ocp)
     rng = np.random.default_rng(3)
     nx, nu, na = ocp.nx, ocp.nu, ocp.na
