@@ -328,8 +328,32 @@ class mpopt:
         return ti, DDx, DDu
 
     # ------------------------------------------------------------------ results
-    def process_results(self, solution, plot: bool = False, scaling: bool = False, residual_x=False, residual_dx=False):
-        return post_process(solution, self, scaling)
+    def init_trajectories(self, phase: int = 0):
+        """Callable ``(z, seg_widths) -> (x, u, t, t0, tf, a)`` of one phase: scaled x / u, times in the OCP's units
+        (the reference returns a CasADi Function with this signature, mpopt.py:857-882)."""
+        def trajectories(z, seg_widths=None):
+            post = post_process({"x": z}, self, scaling=True)
+            widths = None if seg_widths is None or len(seg_widths) == 0 else np.asarray(seg_widths, dtype=float)
+            x, u, t, a = post.get_trajectories(phase, widths=widths)
+            return x, u, t, np.atleast_1d(t[0, 0]), np.atleast_1d(t[-1, 0]), a
+        return trajectories
+
+    def process_results(self, solution, plot: bool = False, scaling: bool = False, residual_x: bool = False,
+                        residual_dx: bool = False):
+        """Post-processor of a solution (mpopt.py:884-981).  ``residual_x`` / ``residual_dx`` evaluate the state and
+        dynamics residuals on the GPU and attach them as ``post.residuals = {"t_x": [ti, res_x], "t_dx": [tdx, res_dx]}``
+        (the reference's ``options["residuals"]``); plotting is out of scope, so ``plot`` is ignored."""
+        post = post_process(solution, self, scaling)
+        post.residuals = None
+        if residual_x or residual_dx:
+            post.residuals = {}
+            if residual_x:
+                _, _, ti, res_x = self.get_states_residuals(solution)
+                post.residuals["t_x"] = [ti, res_x]
+            if residual_dx:
+                tdx, res_dx = self.get_dynamics_residuals(solution)
+                post.residuals["t_dx"] = [tdx, res_dx]
+        return post
 
     def validate(self):
         pass
@@ -349,8 +373,9 @@ class post_process:
                                       "use get_data() / get_data(interpolate=True) and plot the arrays")
         raise AttributeError(name)
 
-    def get_trajectories(self, phase: int = 0):
-        """(x, u, t, a) of one phase, unscaled unless ``scaling`` (mpopt.py:1639-1667)."""
+    def get_trajectories(self, phase: int = 0, widths=None):
+        """(x, u, t, a) of one phase, unscaled unless ``scaling`` (mpopt.py:1639-1667); ``widths``: segment-width
+        fractions of all phases to build the time grid with (default: those of the last solve)."""
         mpo = self.mpo
         tr, o = mpo.transcription, mpo._ocp
         L, N = tr.layout, tr.N
@@ -360,7 +385,7 @@ class post_process:
         U = z[off + o.nx * N:off + (o.nx + o.nu) * N].reshape(o.nu, N).T
         T0, TF = z[L.colT0(phase)] / o.scale_t, z[L.colTF(phase)] / o.scale_t
         A = z[L.colT0(phase) + 2:L.colT0(phase) + 2 + o.na]
-        w = mpo._current_widths()[phase * tr.K:(phase + 1) * tr.K]
+        w = (mpo._current_widths() if widths is None else np.asarray(widths, float))[phase * tr.K:(phase + 1) * tr.K]
         delta = tr.tau1 - tr.tau0
         t = np.empty(N)
         t[0], acc = T0, T0
@@ -432,5 +457,5 @@ def solve(ocp, n_segments=1, poly_orders=9, scheme="LGR", plot=False, solve_dict
     """One-liner of the reference (mpopt.py:4279-4308): returns (optimizer, post-processor)."""
     mpo = mpopt(ocp, n_segments=n_segments, poly_orders=poly_orders, scheme=scheme)
     solution = mpo.solve(**solve_dict)
-    post = mpo.process_results(solution, plot=False)
+    post = mpo.process_results(solution, plot=False, residual_x=residual_x, residual_dx=residual_dx)
     return (mpo, post)

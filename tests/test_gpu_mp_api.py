@@ -204,3 +204,26 @@ def test_states_residuals_on_the_analytic_solution(mp):
         assert (abs(x_all - (-2 * t_all ** 2 + 6 * t_all + 1)) < 1e-3).all()
     finally:
         mp.CollocationRoots._TAU_MIN = -1
+
+
+def test_process_results_residual_flags_and_init_trajectories(mp):
+    """mpopt.py:884-981 (residual_x / residual_dx attach the residual lists) and :857-882 (init_trajectories returns a
+    callable (z, widths) -> (x, u, t, t0, tf, a) with scaled x, u)."""
+    from mpopt_b200.problems import moon_lander
+
+    mpo = mp.mpopt(moon_lander(), 5, 3, "LGR")
+    sol = mpo.solve()
+    post = mpo.process_results(sol, plot=False, residual_x=True, residual_dx=True)
+    assert set(post.residuals) == {"t_x", "t_dx"}
+    ti, res_dx = post.residuals["t_dx"]
+    assert len(res_dx) == 1 and len(res_dx[0]) == 5
+    ti2, res_x = post.residuals["t_x"]
+    assert len(res_x[0]) == 5 and all(np.asarray(r).shape[1] == 2 for r in res_x[0] if r is not None)
+    assert mpo.process_results(sol).residuals is None
+    x, u, t, t0, tf, a = mpo.init_trajectories(0)(sol["x"], mpo._nlp_sw_params)
+    assert x.shape == (16, 2) and u.shape == (16, 1) and t.shape == (16, 1)
+    assert abs(t0[0]) < 1e-12 and abs(tf[0] - t[-1, 0]) < 1e-12 and abs(x[0, 0] - 10.0) < 1e-9
+    # unequal widths move the interior time grid but not its ends
+    w = np.array([0.1, 0.2, 0.3, 0.2, 0.2])
+    x2, u2, t2, *_ = mpo.init_trajectories(0)(sol["x"], w)
+    assert abs(t2[-1, 0] - t[-1, 0]) < 1e-12 and abs(t2[3, 0] - 0.1 * t[-1, 0]) < 1e-12
