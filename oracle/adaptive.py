@@ -222,3 +222,73 @@ class OracleAdaptiveNLP(OracleNLP):
         nb = self.nvar - self.K
         return np.concatenate([np.concatenate([base[ph * nb: (ph + 1) * nb], np.full(self.K, 1.0 / self.K)])
                                for ph in range(self.P)])
+
+    # ------------------------------------------------------------------ Hessian of the Lagrangian (oracle/hessian.py)
+    def _time_dependent(self, ph):
+        """True if the dynamics, path constraints or running cost of the phase depend on t explicitly."""
+        o, one = self.ocp, np.ones(1)
+        x = Vec(Dual(0.7 * one, {("x", s): one}) for s in range(self.nx))
+        u = Vec(Dual(0.6 * one, {("u", c): one}) for c in range(self.nu))
+        a = Vec(Dual(0.5 * one, {("a", m): one}) for m in range(self.na))
+        t = Dual(0.4 * one, {("t",): one})
+        outs = flatten(o.get_dynamics(ph)(x, u, t, a)) + flatten(o.get_running_costs(ph)(x, u, t, a))
+        if self._rows[ph]["nc"]:
+            outs += flatten(o.get_path_constraints(ph)(x, u, t, a))
+        return any(isinstance(e, Dual) and ("t",) in e.der for e in outs)
+
+    def _extra_hessian(self, ph, z, lam_phase, rows, cols, vals):
+        """Second derivatives of  sum lam_R R  over the mid-point residual rows
+        R(k, s, m) = w_k (DI_k[m,:] X(seg k, s) - h_k sx_s f_s(CI_k[m,:] X / sx, CI_k[m,:] U / su, t_m, a / sa)):
+        every node variable of a segment couples with every other one of that segment, with w_k, T0, TF and a.
+        (sum(w) - 1, compI.U and compI.X are linear.)  Time-dependent problems are refused: there t_m, and in the base
+        rows t_i, also depend on every earlier width, which hess_l's node-local variables do not model."""
+        from .dual2 import Dual2
+
+        if self._time_dependent(ph):
+            raise NotImplementedError("Hessian oracle of the adaptive NLP: explicit time dependence is not covered")
+        if not self.mid_residuals:
+            return
+        o, N, K, nx, nu, na = self.ocp, self.N, self.K, self.nx, self.nu, self.na
+        R = self._rows[ph]
+        X, U, T0, TF, A = self._unpack(ph, z)
+        w, wcols = self._widths(ph, z, None)
+        st, delta = o.scale_t, self.tau1 - self.tau0
+        r0 = R["SW"] + 1 + (nu * (N - 1) if R["sw_u"] else 0) + (nx * (N - 1) if R["sw_x"] else 0)
+        for k, d in enumerate(self.po):
+            s0 = int(self.seg_start[k])
+            _, Cm, Dm = self._mid[d]
+            one = np.ones(d)
+            Xl = [[Dual2.variable(X[s0 + j, s] * one, ("x", j, s)) for s in range(nx)] for j in range(d + 1)]
+            Ul = [[Dual2.variable(U[s0 + j, c] * one, ("u", j, c)) for c in range(nu)] for j in range(d + 1)]
+            Ad = [Dual2.variable(A[m] * one, ("a", m)) for m in range(na)]
+            T0d, TFd, Wd = Dual2.variable(T0 * one, ("T0",)), Dual2.variable(TF * one, ("TF",)), Dual2.variable(w[k] * one, ("w",))
+
+            def interp(M, loc, q):
+                acc = loc[0][q] * M[:, 0]
+                for j in range(1, d + 1):
+                    acc = acc + loc[j][q] * M[:, j]
+                return acc
+
+            xi = Vec(interp(Cm, Xl, s) * (1.0 / o.scale_x[s]) for s in range(nx))
+            ui = Vec(interp(Cm, Ul, c) * (1.0 / o.scale_u[c]) for c in range(nu))
+            a = Vec(Ad[m] * (1.0 / o.scale_a[m]) for m in range(na))
+            hk = (TFd - T0d) * (1.0 / (st * delta)) * Wd
+            f = o.get_dynamics(ph)(xi, ui, Dual2(np.zeros(d)), a)
+            f = list(f) if isinstance(f, (list, tuple)) else [f]
+            lag = Dual2(np.zeros(d))
+            for s in range(nx):
+                lam_s = lam_phase[r0 + nx * s0 + s * d: r0 + nx * s0 + (s + 1) * d]
+                lag = lag + (Wd * (interp(Dm, Xl, s) - hk * f[s] * o.scale_x[s])) * lam_s
+
+            def col(key):
+                if key[0] == "x":
+                    return self.colX(ph, s0 + key[1], key[2])
+                if key[0] == "u":
+                    return self.colU(ph, s0 + key[1], key[2])
+                if key[0] == "a":
+                    return self.colA(ph, key[1])
+                return {"T0": self.colT0(ph), "TF": self.colTF(ph), "w": int(wcols[k])}[key[0]]
+
+            for (ka, kb), v in lag.H.items():
+                ca, cb = col(ka), col(kb)
+                rows.append(np.array([max(ca, cb)])), cols.append(np.array([min(ca, cb)])), vals.append(np.array([np.sum(v)]))

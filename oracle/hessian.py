@@ -48,10 +48,12 @@ def hess_l(ora, z, p=None, lam_f=1.0, lam_g=None):
         R = ora._rows[ph]
         base = int(ora.row_off[ph])
         X, U, T0, TF, A = ora._unpack(ph, z)
-        w = p[ph * K: (ph + 1) * K]
+        w, wcols = ora._widths(ph, z, p)  # parameters, or (oracle/adaptive.py) decision variables with columns wcols
         delta = ora.tau1 - ora.tau0
         _, _, sigma, _ = ora._time_grid(ph, T0, TF, w)
         wn = w[ora.node_seg]
+        if wcols is not None:  # h_k = (tf - t0)/delta * w_k is bilinear in (T0 | TF, w_k); sigma is handled by the subclass
+            wn = Dual2.variable(wn, ("w",))
         ones = np.ones(N)
         # raw decision variables as second-order duals, one entry per node
         Xd = [Dual2.variable(X[:, s], ("x", s)) for s in range(nx)]
@@ -62,7 +64,7 @@ def hess_l(ora, z, p=None, lam_f=1.0, lam_g=None):
         u = _V(Ud[c] * (1.0 / o.scale_u[c]) for c in range(nu))
         a = _V(Ad[m] * (1.0 / o.scale_a[m]) for m in range(na))
         t0, tf = T0d * (1.0 / st), TFd * (1.0 / st)  # :175-176
-        h = (tf - t0) * (wn / delta)  # :184
+        h = (tf - t0) * (wn * (1.0 / delta))  # :184
         t = t0 + (tf - t0) * sigma  # :192, :198
         lag = Dual2(np.zeros(N))
         f = _components(o.get_dynamics(ph)(x, u, t, a), nx)
@@ -87,6 +89,8 @@ def hess_l(ora, z, p=None, lam_f=1.0, lam_g=None):
                 return ora.colU(ph, nodes, key[1])
             if key[0] == "a":
                 return ora.colA(ph, key[1])
+            if key[0] == "w":
+                return wcols[ora.node_seg]
             return ora.colT0(ph) if key[0] == "T0" else ora.colTF(ph)
 
         for (ka, kb), v in lag.H.items():
@@ -121,6 +125,8 @@ def hess_l(ora, z, p=None, lam_f=1.0, lam_g=None):
         for (ka, kb), v in theta.H.items():
             ca, cb = tcol(ka), tcol(kb)
             rows.append(np.array([max(ca, cb)])), cols.append(np.array([min(ca, cb)])), vals.append(np.asarray(v, float).reshape(1))
+        if hasattr(ora, "_extra_hessian"):  # constraint blocks a subclass appends to the phase (oracle/adaptive.py)
+            ora._extra_hessian(ph, z, lam[base: base + R["n"]], rows, cols, vals)
 
     if not rows:
         return sp.csr_matrix((ora.n_z, ora.n_z))

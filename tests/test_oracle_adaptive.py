@@ -101,3 +101,42 @@ def test_host_layout_agrees_with_oracle():
             assert L.phases[ph].gSW == ora.row_off[ph] + ora._rows[ph]["SW"]
             assert L.phases[ph].gTC == ora.row_off[ph] + ora._rows[ph]["TC"]
             assert L.colW(ph, K - 1) == ora.colW(ph, K - 1) and L.colT0(ph) == ora.colT0(ph)
+
+
+@pytest.mark.parametrize("problem,K,po", [("moon_lander", 3, 3), ("hyper_sensitive", 3, [4, 2, 3]), ("synthetic_6_3", 2, 3),
+                                          ("two_phase_schwartz", 2, 4)])
+def test_adaptive_hessian_oracle_by_finite_differences(problem, K, po):
+    """Hessian of lam_f f + lam_g . g of the widths-as-variables NLP (the nlp_hess_l CasADi would derive for
+    mpopt_adaptive, mpopt.py:3174-3205): second-order duals with the widths as variables and the dense per-segment
+    coupling of the mid-point residual rows, against central differences of the oracle's own gradient of the Lagrangian.
+    (Head start for the device kernel: DESIGN.md section 8, item 1.)"""
+    import scipy.sparse as sp
+    from oracle.hessian import hess_l
+
+    n = OracleAdaptiveNLP(pr.REGISTRY[problem](), K, po, "LGR")
+    z = adaptive_point(n)
+    rng = np.random.default_rng(5)
+    lam, sig = rng.uniform(-1, 1, n.n_g), 0.7
+    H = hess_l(n, z, None, sig, lam)
+    assert (H.tocoo().row >= H.tocoo().col).all()
+    Hs = (H + sp.tril(H, k=-1).T).toarray()
+    pattern = (H + sp.tril(H, k=-1).T).astype(bool).toarray()
+
+    def grad_lag(zz):
+        return sig * n.grad_f(zz) + n.jac_g(zz).T @ lam
+
+    e = 1e-6
+    for j in range(n.n_z):
+        dz = np.zeros(n.n_z)
+        dz[j] = e
+        col = (grad_lag(z + dz) - grad_lag(z - dz)) / (2 * e)
+        assert np.abs(col - Hs[:, j]).max() <= 1e-6 * max(1.0, np.abs(col).max()), j
+        assert np.abs(col[~pattern[:, j]]).max(initial=0.0) <= 1e-6, j   # nothing outside the structural pattern
+
+
+def test_adaptive_hessian_oracle_refuses_time_dependence():
+    from oracle.hessian import hess_l
+
+    n = OracleAdaptiveNLP(pr.kitchen_sink(), 3, [3, 2, 4], "LGR")
+    with pytest.raises(NotImplementedError):
+        hess_l(n, adaptive_point(n), None, 1.0, np.zeros(n.n_g))
