@@ -61,6 +61,22 @@ def main():
                             colind=J.indices.astype(np.int64), values=J.data, zmin=zmin, zmax=zmax, gmin=gmin, gmax=gmax,
                             z0=ora.initialize_solution())
         print(name, "n_z", ora.n_z, "n_g", ora.n_g, "nnz", J.nnz)
+    # Hessian of the Lagrangian (nlp_hess_l): separate files, so the vectors above stay byte-identical
+    from oracle.hessian import hess_l
+
+    for name, case in CASES.items():
+        path = os.path.join(HERE, name + "_hess.npz")
+        if os.path.exists(path) and "--all" not in sys.argv:
+            continue
+        ora, z, p = build(case)
+        lam = np.random.default_rng(21).uniform(-1, 1, ora.n_g)
+        try:
+            H = hess_l(ora, z, p, 0.75, lam)
+        except NotImplementedError:  # adaptive NLP with explicit time dependence
+            continue
+        np.savez_compressed(path, z=z, p=p, lam_f=0.75, lam_g=lam, rowptr=H.indptr.astype(np.int64),
+                            colind=H.indices.astype(np.int64), values=H.data)
+        print(name + "_hess", "nnz", H.nnz)
 
 
 if __name__ == "__main__":

@@ -57,3 +57,31 @@ def test_cuda_reproduces_golden(libmpx, name):
     for a, b in zip(tr.bounds(), (G["zmin"], G["zmax"], G["gmin"], G["gmax"])):
         assert np.array_equal(a, b)
     assert np.allclose(tr.initial_guess(), G["z0"], rtol=0, atol=1e-15)
+
+
+HESS = sorted(n for n in CASES if os.path.exists(os.path.join(sys_path_golden, n + "_hess.npz")))
+
+
+@pytest.mark.parametrize("name", HESS)
+def test_oracle_reproduces_golden_hessian(name):
+    from oracle.hessian import hess_l
+
+    G = np.load(os.path.join(sys_path_golden, name + "_hess.npz"))
+    ora, _, _ = _M.build(CASES[name])
+    H = hess_l(ora, G["z"], G["p"], float(G["lam_f"]), G["lam_g"])
+    assert np.array_equal(H.indptr, G["rowptr"]) and np.array_equal(H.indices, G["colind"])
+    assert_close(H.data, G["values"], "hess_l values", 1e-12)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n in HESS if len(CASES[n]) == 4])  # the adaptive NLP has no device Hessian yet
+def test_cuda_reproduces_golden_hessian(libmpx, name):
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+
+    problem, K, po, scheme = CASES[name][:4]
+    G = np.load(os.path.join(sys_path_golden, name + "_hess.npz"))
+    tr = Transcription(REGISTRY[problem](), K, po, scheme, drop_exact_zeros=False)
+    rp, ci = tr.hess_structure()
+    assert np.array_equal(rp, G["rowptr"]) and np.array_equal(ci, G["colind"])
+    assert_close(tr.hess_l_values(G["z"], G["p"], float(G["lam_f"]), G["lam_g"]), G["values"], "hess_l values")
