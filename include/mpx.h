@@ -152,6 +152,12 @@ int mpx_eval_f_grad_dev(mpx_plan* plan, const double* d_z, const double* d_p, do
 int mpx_eval_g_jac_dev(mpx_plan* plan, const double* d_z, const double* d_p, double* d_g, double* d_values_or_null,
                        void* stream);
 int mpx_sync(mpx_plan* plan);
+/* -- measurement aids (bench.py, profiles/tools): mpx_gate occupies `stream` for usec microseconds so that a timed
+ *    region can be enqueued completely before the device starts on it (host launch latency stays outside the CUDA
+ *    events); mpx_trace_read returns the per-warp timeline of the last g + jac_g launch of a plan created under
+ *    MPX_TRACE=1 (n_warps records of `slots` 64-bit stamps; out == NULL: only the counts). */
+int mpx_gate(void* stream, double usec);
+int mpx_trace_read(mpx_plan* plan, int64_t* n_warps, int64_t* slots, unsigned long long* out);
 
 /* -- fused evaluation + all-gather over peer memory (multi-GPU, one process per GPU): every store of the g + jac_g
  *    kernel is issued to this GPU's buffers AND to the same offsets of n_peers peer buffers (other GPUs' allocations
@@ -210,6 +216,9 @@ int mpx_eval_state_residuals(mpx_plan* plan, const double* z, const double* p, i
 int mpx_stage(mpx_plan* plan, const double* z, const double* p, int32_t what /* MPX_STAGE_* bits */);
 int mpx_staged(const mpx_plan* plan);                       /* bits valid for the x of the last mpx_stage */
 int mpx_fetch(mpx_plan* plan, int32_t what, double* out);   /* F: 1, GRAD: n_z, G: n_g, JAC / JAC_CCS: nnz doubles */
+/* Hessian of the Lagrangian at the x of the last mpx_stage (no upload of x; staged results stay valid). Any host
+ * entry point that uploads another x (mpx_eval_*) invalidates what is staged: mpx_staged() returns 0 afterwards. */
+int mpx_hess_l_staged(mpx_plan* plan, double lam_f, const double* lam_g, double* values);
 
 /* -- IPOPT C interface (IpStdCInterface.h: Eval_F_CB, Eval_Grad_F_CB, Eval_G_CB, Eval_Jac_G_CB): pass these four
  *    functions to CreateIpoptProblem and a filled mpx_ipopt_data as user_data. Index = int, Number = double,

@@ -323,6 +323,8 @@ struct mpx_plan {
   std::vector<int64_t> h_runs[3];  // shard plans: (offset, count) runs of g / values / grad_f written by this shard
   int staged = 0;                  // MPX_STAGE_* results currently valid in the device buffers (mpx_stage / mpx_fetch)
   DevBuf d_ccs_perm, d_ccs_vals;   // CCS order of the Jacobian values, built on first use
+  DevBuf d_trace;                  // MPX_TRACE=1: timeline records of the K2 kernel (diagnostics), ring of MPX_TRACE_RING launches
+  int64_t trace_seq = 0;
   const MpxProgramEntry* prog = nullptr;
   std::string origin;
   std::vector<MpxPhaseArgs> args;
@@ -1489,7 +1491,46 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     }
   }
   if (p.adaptive) p.origin += ";adaptive";
+  if (const char* te = getenv("MPX_TRACE")) {  // K2 timeline records, read back with mpx_trace_read
+    if (atoi(te) && p.v2_warps > 0 && !p.v4) {
+      const size_t nb = (size_t)MPX_TRACE_RING * p.v2_grid * p.v2_warps * MPX_TRACE_SLOTS * sizeof(unsigned long long);
+      CUDA_TRY(p.d_trace.ensure(nb));
+      CUDA_TRY(cudaMemset(p.d_trace.p, 0, nb));
+    }
+  }
   *out = pp.release();
+  return MPX_OK;
+}
+
+// diagnostics: the timeline records of the last MPX_TRACE_RING K2 launches (MPX_TRACE=1 at plan creation), oldest
+// first: n_warps records (= ring x warps per launch) of MPX_TRACE_SLOTS 64-bit stamps. out == NULL: only the count.
+extern "C" int mpx_trace_read(mpx_plan* p, int64_t* n_warps, int64_t* slots, unsigned long long* out) {
+  if (!p) return fail(MPX_EINVAL, "NULL plan");
+  const int64_t nw = p->d_trace.p ? (int64_t)MPX_TRACE_RING * p->v2_grid * p->v2_warps : 0;
+  if (n_warps) *n_warps = nw;
+  if (slots) *slots = MPX_TRACE_SLOTS;
+  if (out && nw) {
+    CUDA_TRY(cudaSetDevice(p->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, p->d_trace.p, (size_t)nw * MPX_TRACE_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  }
+  return MPX_OK;
+}
+
+// measurement aid: a kernel that occupies the stream for `usec` microseconds, so that a caller can enqueue a whole
+// timed region behind it and keep host launch latency out of the CUDA-event pair (bench.py)
+__global__ void mpx_gate_kernel(unsigned long long ns) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  do {
+    __nanosleep(200);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  } while (t - t0 < ns);
+}
+extern "C" int mpx_gate(void* stream, double usec) {
+  if (usec < 0 || usec > 1e6) return fail(MPX_EINVAL, "mpx_gate: 0 <= usec <= 1e6");
+  mpx_gate_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>((unsigned long long)(usec * 1e3));
+  CUDA_TRY(cudaGetLastError());
   return MPX_OK;
 }
 
@@ -1635,6 +1676,8 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
         CUDA_TRY(p.prog->phases[ph]->gjac4(a, jac, p.spec_deg, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
     } else if (p.v2_warps > 0) {
       a.v4_nbuf = p.v2_nbuf;
+      if (p.d_trace.p)
+        a.trace = p.d_trace.as<unsigned long long>() + (size_t)(p.trace_seq++ % MPX_TRACE_RING) * p.v2_grid * p.v2_warps * MPX_TRACE_SLOTS;
       const size_t sm2 = jac ? p.v2_smem_jac : p.v2_smem_g;
       if (p.rt_spec)
         CUDA_TRY(MpxRtPhase::go(static_cast<const RtSpec*>(p.rt_spec)->f[ph][jac], a, p.v2_grid, p.v2_warps * 32, sm2, st, true));
@@ -1742,6 +1785,7 @@ static int download(mpx_plan& p, int kind, double* dst, const double* src, size_
 static int upload_inputs(mpx_plan& p, const double* z, const double* pw) {
   if (!z || (!pw && p.n_p)) return fail(MPX_EINVAL, "z and p must not be NULL");
   CUDA_TRY(cudaSetDevice(p.device));
+  p.staged = 0;  // every host entry point overwrites d_z (and then d_g / d_vals / d_f / d_grad): nothing staged survives
   if (p.seg_begin == 0 && p.seg_end == p.K) {
     CUDA_TRY(cudaMemcpyAsync(p.d_z.p, z, (size_t)p.n_z * sizeof(double), cudaMemcpyHostToDevice, p.stream));
   } else {  // a shard reads only its own nodes (plus the node it shares with the previous segment) and t0 / tf / a
@@ -2031,6 +2075,21 @@ extern "C" int mpx_eval_hess_l(mpx_plan* p, const double* z, const double* pw, d
   if (rc) return rc;
   rc = upload_inputs(*p, z, pw);
   if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(p->d_lam.p, lam_g, (size_t)p->n_g * sizeof(double), cudaMemcpyHostToDevice, p->stream));
+  rc = launch_hess(*p, p->d_z.as<double>(), p->d_p.as<double>(), lam_f, p->d_lam.as<double>(), p->d_hvals.as<double>(), p->stream);
+  if (rc) return rc;
+  CUDA_TRY(cudaMemcpyAsync(values, p->d_hvals.p, p->h_colind.size() * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+// Hessian at the x of the last mpx_stage (already on the device): no upload of x, staged results stay valid
+extern "C" int mpx_hess_l_staged(mpx_plan* p, double lam_f, const double* lam_g, double* values) {
+  if (!p || !lam_g || !values) return fail(MPX_EINVAL, "NULL argument");
+  if (!p->staged) return fail(MPX_EINVAL, "mpx_hess_l_staged: nothing is staged (call mpx_stage first)");
+  int rc = build_hessian(*p);
+  if (rc) return rc;
+  CUDA_TRY(cudaSetDevice(p->device));
   CUDA_TRY(cudaMemcpyAsync(p->d_lam.p, lam_g, (size_t)p->n_g * sizeof(double), cudaMemcpyHostToDevice, p->stream));
   rc = launch_hess(*p, p->d_z.as<double>(), p->d_p.as<double>(), lam_f, p->d_lam.as<double>(), p->d_hvals.as<double>(), p->stream);
   if (rc) return rc;

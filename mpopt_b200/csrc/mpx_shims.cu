@@ -75,7 +75,7 @@ extern "C" int mpx_ipopt_eval_jac_g(int n, const double* x, int new_x, int m, in
 // Eval_H_CB: lower triangle of sigma * hess f + sum lambda_i hess g_i.  values == NULL: the pattern as triplets.
 extern "C" int mpx_ipopt_eval_h(int n, const double* x, int new_x, double obj_factor, int m, const double* lambda,
                                 int new_lambda, int nele_hess, int* iRow, int* jCol, double* values, void* user_data) {
-  (void)new_x, (void)new_lambda;  // the Hessian kernel is cheap next to the Jacobian: always evaluated from (x, lambda)
+  (void)new_lambda;  // the Hessian kernel is cheap next to the Jacobian: always evaluated from (x, lambda)
   mpx_ipopt_data* d = static_cast<mpx_ipopt_data*>(user_data);
   if (!d || !d->plan || p_missing(d->plan, d->p) || !sizes_ok(d->plan, n, m, -1)) return 0;
   int64_t nnz = 0;
@@ -89,7 +89,10 @@ extern "C" int mpx_ipopt_eval_h(int n, const double* x, int new_x, double obj_fa
     return 1;
   }
   if (!x || !lambda) return 0;
-  return mpx_eval_hess_l(d->plan, x, d->p, obj_factor, lambda, values) == MPX_OK;
+  // eval_h may be the FIRST callback at a new iterate: stage f / grad_f / g / jac_g for this x like the other callbacks
+  // do, so that the callbacks that follow with new_x = 0 fetch results of the same x; then the Hessian at the staged x
+  if (ensure_staged(d, x, new_x, MPX_STAGE_F) != MPX_OK) return 0;
+  return mpx_hess_l_staged(d->plan, obj_factor, lambda, values) == MPX_OK;
 }
 
 // ------------------------------------------------------------------ CasADi external functions

@@ -283,6 +283,15 @@ class Transcription:
     def sync(self):
         _lib.check(self._L.mpx_sync(self._plan))
 
+    def trace(self):
+        """Timeline records of the last g + jac_g launch (plan created under MPX_TRACE=1): uint64 [warps, slots]."""
+        nw, ns = C.c_int64(), C.c_int64()
+        _lib.check(self._L.mpx_trace_read(self._plan, C.byref(nw), C.byref(ns), None))
+        out = np.zeros((int(nw.value), int(ns.value)), dtype=np.uint64)
+        if out.size:
+            _lib.check(self._L.mpx_trace_read(self._plan, None, None, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out
+
     @property
     def launches(self):
         return int(self._L.mpx_launch_count(self._plan))

@@ -100,6 +100,55 @@ def test_ipopt_callbacks_match_oracle(libmpx):
 
 
 @pytest.mark.gpu
+def test_ipopt_eval_h_first_at_a_new_iterate_restages(libmpx):
+    """eval_h may be the first callback at a new x: the callbacks that follow with new_x = 0 must see THAT x."""
+    from mpopt_b200 import _lib
+    from mpopt_b200.problems import kitchen_sink
+    from oracle.hessian import hess_l
+
+    tr, ora, z, w = _setup(kitchen_sink, 4, [3, 5, 4, 3], "LGR")
+    n, m, nnz = tr.n_z, tr.n_g, tr.nnz
+    d = _lib.IpoptData(tr._plan, _lib.ptr(w))
+    ud = C.byref(d)
+    f, g, vals = np.zeros(1), np.zeros(m), np.zeros(nnz)
+    assert libmpx.mpx_ipopt_eval_f(n, _lib.ptr(z), 1, _lib.ptr(f), ud) == 1  # iterate 1
+    z2 = z + 0.01 * np.random.default_rng(2).standard_normal(n)
+    lam = np.random.default_rng(1).uniform(-1, 1, m)
+    H = hess_l(ora, z2, w, 0.7, lam)
+    hv = np.zeros(H.nnz)
+    assert libmpx.mpx_ipopt_eval_h(n, _lib.ptr(z2), 1, 0.7, m, _lib.ptr(lam), 1, H.nnz, None, None, _lib.ptr(hv), ud) == 1
+    assert_close(hv, H.data, "eval_h at the new iterate")
+    assert libmpx.mpx_ipopt_eval_g(n, _lib.ptr(z2), 0, m, _lib.ptr(g), ud) == 1
+    assert libmpx.mpx_ipopt_eval_jac_g(n, _lib.ptr(z2), 0, m, nnz, None, None, _lib.ptr(vals), ud) == 1
+    assert libmpx.mpx_ipopt_eval_f(n, _lib.ptr(z2), 0, _lib.ptr(f), ud) == 1
+    assert_close(g, ora.g(z2, w), "g after eval_h(new_x)")
+    assert_close(vals, ora.jac_g(z2, w).data, "jac_g after eval_h(new_x)")
+    assert abs(f[0] - ora.f(z2, w)) <= 1e-10 * max(1.0, abs(ora.f(z2, w)))
+
+
+@pytest.mark.gpu
+def test_host_evaluation_invalidates_staged_results(libmpx):
+    """stage at z, a direct mpx_eval_g at another z, then a fetch: the stale staged result must not come back."""
+    from mpopt_b200 import _lib
+    from mpopt_b200.problems import kitchen_sink
+
+    tr, ora, z, w = _setup(kitchen_sink, 4, [3, 5, 4, 3], "LGR")
+    n, m = tr.n_z, tr.n_g
+    assert libmpx.mpx_stage(tr._plan, _lib.ptr(z), _lib.ptr(w), _lib.MPX_STAGE_G | _lib.MPX_STAGE_JAC) == 0
+    assert libmpx.mpx_staged(tr._plan) & _lib.MPX_STAGE_G
+    z2 = z + 0.05
+    g2 = tr.g(z2, w)
+    assert_close(g2, ora.g(z2, w), "direct g")
+    assert libmpx.mpx_staged(tr._plan) == 0
+    g = np.zeros(m)
+    assert libmpx.mpx_fetch(tr._plan, _lib.MPX_STAGE_G, _lib.ptr(g)) == _lib.MPX_EINVAL
+    # the IPOPT callback with new_x = 0 notices and re-stages with the x it is handed
+    d = _lib.IpoptData(tr._plan, _lib.ptr(w))
+    assert libmpx.mpx_ipopt_eval_g(n, _lib.ptr(z), 0, m, _lib.ptr(g), C.byref(d)) == 1
+    assert_close(g, ora.g(z, w), "g re-staged")
+
+
+@pytest.mark.gpu
 def test_casadi_externals_match_oracle(libmpx):
     from mpopt_b200 import _lib
     from mpopt_b200.problems import two_phase_schwartz
