@@ -152,6 +152,24 @@ int mpx_eval_f_grad_dev(mpx_plan* plan, const double* d_z, const double* d_p, do
 int mpx_eval_g_jac_dev(mpx_plan* plan, const double* d_z, const double* d_p, double* d_g, double* d_values_or_null,
                        void* stream);
 int mpx_sync(mpx_plan* plan);
+/* -- the host hop. The reference's consumers (IPOPT through CasADi, mpopt.py:804) own host buffers, so every
+ *    evaluation ends with a device-to-host copy that dwarfs the kernel (105 MB of Jacobian values at the headline
+ *    size: 2 ms over PCIe 5 against a 19 us kernel). Two things help a caller whose buffers are stable:
+ *    mpx_host_register pins a caller-owned range (cudaHostRegister, mapped) for the life of the plan or until
+ *    mpx_host_unregister -- copies into it run at full link speed instead of through the driver's bounce buffers --
+ *    and mpx_eval_jac_g_dynamic then moves only the n_dynamic entries that depend on z or p (the off-block partials,
+ *    the merged D diagonals, d/dT0, d/dTF, path and terminal rows): the first call on a registered
+ *    buffer is a full mpx_eval_jac_g, later ones rewrite just those entries in place. The caller must not modify
+ *    `values` in between, and must unregister before freeing the memory. Unregistered `values`: plain full fetch.
+ *    mpx_eval_jac_g_packed returns the dynamic entries packed (n_dynamic doubles, positions from
+ *    mpx_jac_dynamic_positions, ascending CSR order) for callers that keep their own copy of the constants. */
+int mpx_host_register(mpx_plan* plan, void* ptr, int64_t bytes);
+int mpx_host_unregister(mpx_plan* plan, void* ptr);
+int mpx_jac_dynamic_count(mpx_plan* plan, int64_t* n_dynamic);
+int mpx_jac_dynamic_positions(mpx_plan* plan, int32_t* positions /* n_dynamic */);
+int mpx_eval_jac_g_dynamic(mpx_plan* plan, const double* z, const double* p, double* g_or_null, double* values);
+int mpx_eval_jac_g_packed(mpx_plan* plan, const double* z, const double* p, double* g_or_null, double* packed);
+
 /* -- measurement aids (bench.py, profiles/tools): mpx_gate occupies `stream` for usec microseconds so that a timed
  *    region can be enqueued completely before the device starts on it (host launch latency stays outside the CUDA
  *    events); mpx_trace_read returns the per-warp timeline of the last g + jac_g launch of a plan created under

@@ -92,6 +92,12 @@ PROTOTYPES = {
     "mpx_staged": (C.c_int, [C.c_void_p]),
     "mpx_fetch": (C.c_int, [C.c_void_p, C.c_int32, c_f64p]),
     "mpx_hess_l_staged": (C.c_int, [C.c_void_p, C.c_double, c_f64p, c_f64p]),
+    "mpx_host_register": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "mpx_host_unregister": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mpx_jac_dynamic_count": (C.c_int, [C.c_void_p, c_i64p]),
+    "mpx_jac_dynamic_positions": (C.c_int, [C.c_void_p, c_i32p]),
+    "mpx_eval_jac_g_dynamic": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "mpx_eval_jac_g_packed": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p]),
     "mpx_gate": (C.c_int, [C.c_void_p, C.c_double]),
     "mpx_trace_read": (C.c_int, [C.c_void_p, c_i64p, c_i64p, C.POINTER(C.c_uint64)]),
     "mpx_ipopt_eval_f": (C.c_int, [C.c_int, c_f64p, C.c_int, c_f64p, C.c_void_p]),

@@ -122,6 +122,23 @@ __global__ void mpx_compact_kernel(const double* __restrict__ full, const int64_
   if (i < n) out[i] = full[map[i]];
 }
 
+// dynamic fetch: copy only the z- / p-dependent Jacobian entries straight into the caller's (registered, mapped) host
+// buffer over PCIe; everything else in that buffer is constant and was written by an earlier full fetch
+__global__ void mpx_scatter_dyn_kernel(const double* __restrict__ vals, const int32_t* __restrict__ pos,
+                                       double* __restrict__ host_vals, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int32_t e = pos[i];
+    host_vals[e] = vals[e];
+  }
+}
+// the same entries gathered into a contiguous device buffer (the variant that ships them with ONE device-to-host copy)
+__global__ void mpx_gather_dyn_kernel(const double* __restrict__ vals, const int32_t* __restrict__ pos,
+                                      double* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = vals[pos[i]];
+}
+
 // state residual by quadrature (mpopt.compute_states_from_solution_dynamics, mpopt.py:989-1076): per segment, the
 // Lagrange interpolant of F = h Sx f through the segment's own target points is integrated from tau0 to every target
 // point (Gauss-Legendre, exact for the interpolant), x_int = x(segment start) + integral, residual = x_I - x_int.
@@ -323,6 +340,13 @@ struct mpx_plan {
   std::vector<int64_t> h_runs[3];  // shard plans: (offset, count) runs of g / values / grad_f written by this shard
   int staged = 0;                  // MPX_STAGE_* results currently valid in the device buffers (mpx_stage / mpx_fetch)
   DevBuf d_ccs_perm, d_ccs_vals;   // CCS order of the Jacobian values, built on first use
+  // host buffers the caller has registered (mpx_host_register): pinned + mapped, so that copies run at full PCIe speed
+  // and the dynamic fetch can write the z-dependent entries straight into them
+  struct HostReg { char* base; size_t bytes; char* dev; bool primed; };
+  std::vector<HostReg> regs;
+  DevBuf d_dyn_pos, d_dyn_vals;    // positions (CSR order, int32) of the z- / p-dependent Jacobian entries; gathered values
+  std::vector<int32_t> h_dyn_pos;
+  int64_t n_dyn = -1;
   DevBuf d_trace;                  // MPX_TRACE=1: timeline records of the K2 kernel (diagnostics), ring of MPX_TRACE_RING launches
   int64_t trace_seq = 0;
   const MpxProgramEntry* prog = nullptr;
@@ -332,6 +356,7 @@ struct mpx_plan {
   int smem_gjac = 0, smem_g = 0, smem_fgrad = 0;
   bool smem_too_big = false;
   ~mpx_plan() {
+    for (auto& r : regs) cudaHostUnregister(r.base);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -1832,6 +1857,153 @@ extern "C" int mpx_eval_jac_g(mpx_plan* p, const double* z, const double* pw, do
   if (rc) return rc;
   if (g && (rc = download(*p, 0, g, p->d_g.as<double>(), (size_t)p->n_g))) return rc;
   if ((rc = download(*p, 1, values, p->d_vals.as<double>(), (size_t)p->nnz))) return rc;
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+// ------------------------------------------------------------------ host hop: registered buffers, dynamic fetch
+extern "C" int mpx_host_register(mpx_plan* p, void* ptr, int64_t bytes) {
+  if (!p || !ptr || bytes <= 0) return fail(MPX_EINVAL, "mpx_host_register: NULL pointer or empty range");
+  CUDA_TRY(cudaSetDevice(p->device));
+  for (auto& r : p->regs)
+    if (r.base == (char*)ptr && r.bytes == (size_t)bytes) return MPX_OK;
+  CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
+  void* dev = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&dev, ptr, 0);
+  if (e != cudaSuccess) {
+    cudaHostUnregister(ptr);
+    return fail(MPX_ECUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e));
+  }
+  p->regs.push_back({(char*)ptr, (size_t)bytes, (char*)dev, false});
+  return MPX_OK;
+}
+extern "C" int mpx_host_unregister(mpx_plan* p, void* ptr) {
+  if (!p || !ptr) return fail(MPX_EINVAL, "mpx_host_unregister: NULL argument");
+  for (size_t i = 0; i < p->regs.size(); ++i)
+    if (p->regs[i].base == (char*)ptr) {
+      CUDA_TRY(cudaSetDevice(p->device));
+      CUDA_TRY(cudaStreamSynchronize(p->stream));
+      CUDA_TRY(cudaHostUnregister(ptr));
+      p->regs.erase(p->regs.begin() + i);
+      return MPX_OK;
+    }
+  return fail(MPX_EINVAL, "mpx_host_unregister: that pointer is not registered with this plan");
+}
+static mpx_plan::HostReg* find_reg(mpx_plan& p, const void* ptr, size_t bytes) {
+  for (auto& r : p.regs)
+    if ((const char*)ptr >= r.base && (const char*)ptr + bytes <= r.base + r.bytes) return &r;
+  return nullptr;
+}
+
+// positions of the Jacobian entries that depend on z or p (everything else is a table entry or +-1): in the defect
+// rows F(s, i) every entry outside the row's own D block, plus the block's diagonal entry when d f_s / d x_s is not
+// identically zero; all of the path and terminal rows.  Slope, mid-point, slope-continuity and event rows are constant
+// (mpopt.py:321, :357-360, :408, :484-519).
+static int build_dynamic(mpx_plan& p) {
+  if (p.n_dyn >= 0) return MPX_OK;
+  if (p.adaptive) return fail(MPX_EINVAL, "the dynamic fetch is not available for the adaptive NLP (its D blocks scale with the widths)");
+  if (p.nnz >= (int64_t)1 << 31) return fail(MPX_ELIMIT, "the dynamic fetch indexes the Jacobian with 32 bits");
+  const int nx = p.nx, nu = p.nu, nv = nx + nu + p.na, N = p.N;
+  std::vector<int> nseg(N);
+  for (int k = 0; k < p.K; ++k)
+    for (int r = (k == 0 ? 0 : 1); r <= p.po[k]; ++r) nseg[p.seg_start[k] + r] = k;
+  std::vector<int32_t>& pos = p.h_dyn_pos;
+  pos.clear();
+  for (int ph = 0; ph < p.P; ++ph) {
+    const PhaseLayout& L = p.ph[ph];
+    for (int s = 0; s < nx; ++s) {
+      const bool diag = L.pat_f[(size_t)s * nv + s] != 0;
+      for (int i = 0; i < N; ++i) {
+        const int k = nseg[i];
+        const int64_t c0 = L.zoff + (int64_t)s * N + p.seg_start[k], c1 = c0 + p.po[k], cd = L.zoff + (int64_t)s * N + i;
+        const int64_t r = L.gF + (int64_t)s * N + i;
+        for (int64_t e = p.rowptr[r]; e < p.rowptr[r + 1]; ++e) {
+          const int64_t c = p.colind[e];
+          if (c < c0 || c > c1 || (diag && c == cd)) pos.push_back((int32_t)e);
+        }
+      }
+    }
+    for (int64_t r = L.gC; r < L.gC + (int64_t)L.nc * N; ++r)
+      for (int64_t e = p.rowptr[r]; e < p.rowptr[r + 1]; ++e) pos.push_back((int32_t)e);
+    for (int64_t r = L.gTC; r < L.gTC + L.ntc; ++r)
+      for (int64_t e = p.rowptr[r]; e < p.rowptr[r + 1]; ++e) pos.push_back((int32_t)e);
+  }
+  std::sort(pos.begin(), pos.end());
+  CUDA_TRY(cudaSetDevice(p.device));
+  CUDA_TRY(p.d_dyn_pos.ensure(std::max<size_t>(pos.size(), 1) * sizeof(int32_t)));
+  CUDA_TRY(cudaMemcpy(p.d_dyn_pos.p, pos.data(), pos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  p.n_dyn = (int64_t)pos.size();
+  return MPX_OK;
+}
+
+extern "C" int mpx_jac_dynamic_count(mpx_plan* p, int64_t* n_dynamic) {
+  if (!p || !n_dynamic) return fail(MPX_EINVAL, "NULL argument");
+  int rc = build_dynamic(*p);
+  if (rc) return rc;
+  *n_dynamic = p->n_dyn;
+  return MPX_OK;
+}
+extern "C" int mpx_jac_dynamic_positions(mpx_plan* p, int32_t* pos) {
+  if (!p || !pos) return fail(MPX_EINVAL, "NULL argument");
+  int rc = build_dynamic(*p);
+  if (rc) return rc;
+  memcpy(pos, p->h_dyn_pos.data(), p->h_dyn_pos.size() * sizeof(int32_t));
+  return MPX_OK;
+}
+
+// g + jac_g into caller-owned host buffers, moving only what changed: `values` must be a buffer registered with
+// mpx_host_register.  The first call on a registered buffer (and every call on an unregistered one) is a full
+// mpx_eval_jac_g, which also writes the constant entries; later calls evaluate on the device and store the n_dynamic
+// z- / p-dependent entries straight into the buffer (mapped host memory, PCIe writes from the kernel) -- 32 % of the
+// bytes at the headline size.  The caller must not modify `values` between calls (IPOPT does not).
+extern "C" int mpx_eval_jac_g_dynamic(mpx_plan* p, const double* z, const double* pw, double* g, double* values) {
+  if (!p || !values) return fail(MPX_EINVAL, "NULL argument");
+  const bool shard = p->seg_begin != 0 || p->seg_end != p->K;
+  mpx_plan::HostReg* reg = shard ? nullptr : find_reg(*p, values, (size_t)p->nnz * sizeof(double));
+  if (!reg || !reg->primed || p->adaptive) {
+    int rc = mpx_eval_jac_g(p, z, pw, g, values);
+    if (rc == MPX_OK && reg) reg->primed = true;
+    return rc;
+  }
+  int rc = build_dynamic(*p);
+  if (rc) return rc;
+  rc = upload_inputs(*p, z, pw);
+  if (rc) return rc;
+  rc = launch_g_jac(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_g.as<double>(), p->d_vals.as<double>(), p->stream);
+  if (rc) return rc;
+  if (g && (rc = download(*p, 0, g, p->d_g.as<double>(), (size_t)p->n_g))) return rc;
+  if (p->n_dyn > 0) {
+    double* hv = reinterpret_cast<double*>(reg->dev + ((char*)values - reg->base));
+    mpx_scatter_dyn_kernel<<<(unsigned)((p->n_dyn + 255) / 256), 256, 0, p->stream>>>(p->d_vals.as<double>(),
+                                                                                   p->d_dyn_pos.as<int32_t>(), hv, p->n_dyn);
+    CUDA_TRY(cudaGetLastError());
+    ++p->launches;
+  }
+  CUDA_TRY(cudaStreamSynchronize(p->stream));
+  return MPX_OK;
+}
+
+// variant B of the dynamic fetch (for comparison and for buffers that cannot be mapped): gather the dynamic entries
+// on the device, ONE contiguous device-to-host copy into plan-owned pinned memory; the caller scatters them with
+// mpx_jac_dynamic_positions (or keeps them packed).  packed: n_dynamic doubles.
+extern "C" int mpx_eval_jac_g_packed(mpx_plan* p, const double* z, const double* pw, double* g, double* packed) {
+  if (!p || !packed) return fail(MPX_EINVAL, "NULL argument");
+  int rc = build_dynamic(*p);
+  if (rc) return rc;
+  rc = upload_inputs(*p, z, pw);
+  if (rc) return rc;
+  rc = launch_g_jac(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_g.as<double>(), p->d_vals.as<double>(), p->stream);
+  if (rc) return rc;
+  if (g && (rc = download(*p, 0, g, p->d_g.as<double>(), (size_t)p->n_g))) return rc;
+  CUDA_TRY(p->d_dyn_vals.ensure(std::max<int64_t>(p->n_dyn, 1) * sizeof(double)));
+  if (p->n_dyn > 0) {
+    mpx_gather_dyn_kernel<<<(unsigned)((p->n_dyn + 255) / 256), 256, 0, p->stream>>>(p->d_vals.as<double>(),
+                                                                                  p->d_dyn_pos.as<int32_t>(),
+                                                                                  p->d_dyn_vals.as<double>(), p->n_dyn);
+    CUDA_TRY(cudaGetLastError());
+    ++p->launches;
+    CUDA_TRY(cudaMemcpyAsync(packed, p->d_dyn_vals.p, (size_t)p->n_dyn * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+  }
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;
 }

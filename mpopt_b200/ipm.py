@@ -58,9 +58,18 @@ def _inertia(ldu, ipiv):
     return pos, neg, zero
 
 
-def solve_nlp(f, grad_f, g, jac_g, hess_l, x0, lbx, ubx, lbg, ubg, tol=1e-9, max_iter=500, mu0=0.1, lam_g0=None,
-              verbose=False, acceptable_tol=1e-6, acceptable_iter=15):
-    """Minimise f(x) s.t. lbg <= g(x) <= ubg, lbx <= x <= ubx.  Returns IpmResult(x, f, g, lam_g, success, iter, err)."""
+def solve_nlp(*args, **kw):
+    """See :func:`_solve_nlp` (same arguments)."""
+    with np.errstate(invalid="ignore", over="ignore", divide="ignore"):  # infinite bounds take part in masked arithmetic
+        return _solve_nlp(*args, **kw)
+
+
+def _solve_nlp(f, grad_f, g, jac_g, hess_l, x0, lbx, ubx, lbg, ubg, tol=1e-9, max_iter=500, mu0=0.1, lam_g0=None,
+              verbose=False, acceptable_tol=1e-6, acceptable_iter=15, bound_push=1e-2):
+    """Minimise f(x) s.t. lbg <= g(x) <= ubg, lbx <= x <= ubx.  Returns IpmResult(x, f, g, lam_g, success, iter, err).
+
+    Warm start (IPOPT's warm_start_init_point): pass the previous ``lam_g`` as ``lam_g0`` together with a small ``mu0``
+    and ``bound_push`` (e.g. 1e-7 / 1e-9) so that the starting point is not pushed away from its active bounds."""
     x = np.array(x0, dtype=float)
     lbx, ubx, lbg, ubg = (np.asarray(v, dtype=float) for v in (lbx, ubx, lbg, ubg))
     n_all, m_all = x.size, lbg.size
@@ -78,7 +87,7 @@ def solve_nlp(f, grad_f, g, jac_g, hess_l, x0, lbx, ubx, lbg, ubg, tol=1e-9, max
 
     def push(y):
         y = y.copy()
-        k1 = k2 = 1e-2
+        k1 = k2 = float(bound_push)
         pl = np.where(hasL & hasU, np.minimum(k1 * np.maximum(1.0, np.abs(L)), k2 * (U - L)), k1 * np.maximum(1.0, np.abs(L)))
         pu = np.where(hasL & hasU, np.minimum(k1 * np.maximum(1.0, np.abs(U)), k2 * (U - L)), k1 * np.maximum(1.0, np.abs(U)))
         lo = np.where(hasL, L + pl, -np.inf)
@@ -91,7 +100,11 @@ def solve_nlp(f, grad_f, g, jac_g, hess_l, x0, lbx, ubx, lbg, ubg, tol=1e-9, max
         return xx, y[n:]
 
     y = push(np.concatenate([x[free], g(x)[ie]]))
-    zL, zU = np.where(hasL, 1.0, 0.0), np.where(hasU, 1.0, 0.0)
+    if lam_g0 is None:
+        zL, zU = np.where(hasL, 1.0, 0.0), np.where(hasU, 1.0, 0.0)
+    else:  # warm start: duals on the central path of the starting barrier parameter
+        zL = np.where(hasL, mu0 / np.where(hasL, y - L, 1.0), 0.0)
+        zU = np.where(hasU, mu0 / np.where(hasU, U - y, 1.0), 0.0)
     lam = np.zeros(m) if lam_g0 is None else np.array(lam_g0, dtype=float)
     mu = float(mu0)
     filt, filt_mu, th_max, th_min = [], None, np.inf, 0.0
@@ -274,5 +287,10 @@ def solve_nlp(f, grad_f, g, jac_g, hess_l, x0, lbx, ubx, lbg, ubg, tol=1e-9, max
         dU = np.where(hasU, U - y, 1.0)
         zL = np.where(hasL, np.clip(zL, mu / (ks * dL), ks * mu / dL), 0.0)
         zU = np.where(hasU, np.clip(zU, mu / (ks * dU), ks * mu / dU), 0.0)
-    lam_full = lam.copy()
-    return IpmResult(x=xx, f=fv, g=gv, lam_g=lam_full, success=bool(ok), iter=it, err=float(err0), mu=mu)
+    # multipliers in IPOPT's convention: grad f + J^T lam_g + lam_x = 0, lam > 0 on an active upper bound
+    lam_x = np.zeros(n_all)
+    lam_x[free] = (zU - zL)[:n]
+    if fixed.any():
+        r = np.asarray(grad_f(xx), dtype=float) + sp.csr_matrix(jac_g(xx)).T @ lam
+        lam_x[fixed] = -r[fixed]
+    return IpmResult(x=xx, f=fv, g=gv, lam_g=lam.copy(), lam_x=lam_x, success=bool(ok), iter=it, err=float(err0), mu=mu)

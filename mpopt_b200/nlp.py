@@ -168,6 +168,37 @@ class Transcription:
         _lib.check(self._L.mpx_eval_jac_g(self._plan, _lib.ptr(z), _lib.ptr(p), _lib.ptr(g_out), _lib.ptr(out)))
         return out
 
+    # ---- the host hop (include/mpx.h): registered caller buffers, dynamic fetch
+    def host_register(self, array):
+        """Pin + map a caller-owned numpy array for the life of the plan (or until ``host_unregister``)."""
+        _lib.check(self._L.mpx_host_register(self._plan, array.ctypes.data, array.nbytes))
+
+    def host_unregister(self, array):
+        _lib.check(self._L.mpx_host_unregister(self._plan, array.ctypes.data))
+
+    def jac_g_values_dynamic(self, z, p=None, out=None, g_out=None):
+        """Like ``jac_g_values`` into a registered ``out``: after the first call only the z- / p-dependent entries are
+        rewritten (``out`` must not be modified in between)."""
+        z, p = self._zp(z, p)
+        _lib.check(self._L.mpx_eval_jac_g_dynamic(self._plan, _lib.ptr(z), _lib.ptr(p), _lib.ptr(g_out), _lib.ptr(out)))
+        return out
+
+    def dynamic_positions(self):
+        """CSR positions (ascending, int32) of the Jacobian entries that depend on z or p."""
+        n = C.c_int64()
+        _lib.check(self._L.mpx_jac_dynamic_count(self._plan, C.byref(n)))
+        pos = np.empty(int(n.value), np.int32)
+        if pos.size:
+            _lib.check(self._L.mpx_jac_dynamic_positions(self._plan, _lib.ptr(pos, _lib.c_i32p)))
+        return pos
+
+    def jac_g_packed(self, z, p=None, out=None, g_out=None):
+        """The dynamic entries only, packed in the order of ``dynamic_positions()``."""
+        z, p = self._zp(z, p)
+        out = np.empty(len(self.dynamic_positions())) if out is None else out
+        _lib.check(self._L.mpx_eval_jac_g_packed(self._plan, _lib.ptr(z), _lib.ptr(p), _lib.ptr(g_out), _lib.ptr(out)))
+        return out
+
     def jac_g(self, z, p=None):
         import scipy.sparse as sp
 

@@ -4,9 +4,11 @@ The reference hands a symbolic NLP to ``ca.nlpsol(name, "ipopt", ...)`` (/root/r
 calls the returned object as ``solver(x0=, p=, lbx=, ubx=, lbg=, ubg=, lam_x0=, lam_g0=)`` getting the dict
 ``{x, f, g, lam_x, lam_g, lam_p}`` back (:804).  CasADi and IPOPT are not installed in this image, so:
 
-* ``ScipyNlpSolver`` -- the default here: SciPy SLSQP (small problems) or trust-constr (sparse, exact Lagrangian
-  Hessian from ``Transcription.hess_l``) driving ``Transcription.f / grad_f / g / jac_g``;  same call signature and
-  result keys.
+* ``ScipyNlpSolver`` -- same call signature and result keys, driving ``Transcription.f / grad_f / g / jac_g /
+  hess_l``.  Methods (``options["method"]``): ``"ipm"`` (default when the exact Hessian kernel is available and the
+  KKT system is small enough to factorise densely) -- the interior-point method of ``mpopt_b200.ipm``, which reproduces
+  the optimal objectives stored in the reference's notebooks to 1e-7 .. 1e-4 (tests/anchors.py); ``"SLSQP"`` and
+  ``"trust-constr"`` -- SciPy's solvers (the adaptive NLP, which has no Hessian kernel, uses these).
 * ``casadi_callbacks`` -- when ``import casadi`` succeeds, wraps the evaluators as ``ca.Callback`` objects with the
   Jacobian sparsity declared, ready for ``ca.nlpsol`` (untested here: no CasADi in the image).
 
@@ -46,9 +48,23 @@ class ScipyNlpSolver:
         fobj = lambda z: tr.f(z, p)
         fgrad = lambda z: tr.grad_f(z, p)
         eq = lbg == ubg
-        method = self.options.get("method", "SLSQP" if n_z <= 600 else "trust-constr")
+        has_hess = not getattr(tr, "adaptive", False)
+        n_ineq = int((~eq).sum())
+        default = "ipm" if (has_hess and n_z + n_g + n_ineq <= 6000) else ("SLSQP" if n_z <= 600 else "trust-constr")
+        method = self.options.get("method", default)
         max_iter = int(self.options.get("ipopt.max_iter", self.options.get("max_iter", 500)))
         x0 = np.clip(x0, lbx, ubx)
+        if method == "ipm":
+            from .ipm import solve_nlp
+
+            r = solve_nlp(fobj, fgrad, lambda z: gj(z)[0], lambda z: gj(z)[1], lambda z, lf, lg: tr.hess_l(z, p, lf, lg),
+                          x0, lbx, ubx, lbg, ubg, tol=float(self.options.get("tol", self.options.get("ipopt.tol", 1e-8))),
+                          max_iter=max_iter, lam_g0=lam_g0,
+                          acceptable_tol=float(self.options.get("ipopt.acceptable_tol", self.options.get("acceptable_tol", 1e-4))))
+            self.stats = {"success": bool(r.success), "status": "converged" if r.success else "not converged",
+                          "iter_count": int(r.iter), "method": method}
+            return {"x": r.x, "f": float(r.f), "g": np.asarray(r.g), "lam_x": r.lam_x, "lam_g": r.lam_g,
+                    "lam_p": np.zeros(tr.n_p)}
         if method == "SLSQP":
             cons = []
             if eq.any():

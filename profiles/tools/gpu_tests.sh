@@ -1,6 +1,4 @@
 #!/bin/bash
-TAG=${1:-tests}
-OUT=gpurun_out/$TAG
-mkdir -p $OUT
-( time timeout 1200 python -m pytest tests -q -m gpu ) > $OUT/pytest_gpu.log 2>&1
-tail -40 $OUT/pytest_gpu.log | cut -c1-300
+mkdir -p gpurun_out/t
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/t/pytest.log 2>&1
+tail -15 gpurun_out/t/pytest.log
