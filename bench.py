@@ -267,8 +267,11 @@ def run_cuda(args):
             pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
         except Exception:
             pass
-    K = WORKLOAD["n_segments"]
-    Kt = K * world  # weak scaling: 4096 segments per GPU
+    # N > 1: the headline scales WEAKLY (n_segments per GPU, one NLP of N x n_segments); config 4 -- BASELINE.json's
+    # "sharded 1/2/4/8" configuration -- scales STRONGLY (one NLP of 8192 segments split over the GPUs)
+    strong = world > 1 and args.config == "4"
+    K = WORKLOAD["n_segments"] // world if strong else WORKLOAD["n_segments"]
+    Kt = K * world
     deg, scheme = poly_orders_of(WORKLOAD, Kt), WORKLOAD["scheme"]
     if world > 1 and not isinstance(deg, int):
         raise SystemExit("bench.py --gpus N > 1 needs a uniform-degree configuration")
@@ -327,11 +330,23 @@ def run_cuda(args):
     # cudaLaunchKernelEx, ~10 us per call) is not inside the event pair; the first launch still pays its full,
     # non-overlapped prologue
     gate_us = 0.0 if args.no_gate else min(2000.0, 150.0 + 15.0 * args.steps)
+    graph = None
+    if args.graph:  # the K launches captured once into a CUDA graph (programmatic edges kept), ONE graph launch timed
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            for i in range(args.steps):
+                step(i)
+        graph.replay()
+        barrier()
+        l0 = tr.launches - args.steps
     if gate_us:
         tr._L.mpx_gate(sp, gate_us)
     e0.record(stream)
-    for i in range(args.steps):
-        step(i)
+    if graph is not None:
+        graph.replay()
+    else:
+        for i in range(args.steps):
+            step(i)
     e1.record(stream)
     barrier()
     launches = tr.launches - l0
@@ -355,46 +370,87 @@ def run_cuda(args):
     #      per evaluation orders the ranks); (b) baseline: the same shards + one NCCL all-gather of g / CSR values.
     allgather = allgather_nccl = None
     if world > 1 and not args.no_allgather:
-        def verify(g_t, v_t):  # equal to a plain single-GPU evaluation of the whole NLP, bit for bit
-            full = Transcription(ocp, Kt, deg, scheme, device=local)
-            g_ref = torch.empty(n_g, dtype=torch.float64, device=dev)
-            v_ref = torch.empty(nnz, dtype=torch.float64, device=dev)
+        full = Transcription(ocp, Kt, deg, scheme, device=local)  # the same NLP on ONE GPU: the check and the yardstick
+        g_ref = torch.empty(n_g, dtype=torch.float64, device=dev)
+        v_ref = torch.empty(nnz, dtype=torch.float64, device=dev)
+        f_ref = torch.zeros(1, dtype=torch.float64, device=dev)
+        grad_ref = torch.empty(n_z, dtype=torch.float64, device=dev)
+        full.g_jac_dev(z_d[0].data_ptr(), p_d.data_ptr(), g_ref.data_ptr(), v_ref.data_ptr(), sp)
+        full.f_grad_dev(z_d[0].data_ptr(), p_d.data_ptr(), f_ref.data_ptr(), grad_ref.data_ptr(), sp)
+        torch.cuda.synchronize()
+        for i in range(3):
             full.g_jac_dev(z_d[0].data_ptr(), p_d.data_ptr(), g_ref.data_ptr(), v_ref.data_ptr(), sp)
-            torch.cuda.synchronize()
-            okt = torch.tensor([int(torch.equal(g_ref, g_t) and torch.equal(v_ref, v_t))], device=dev)
+        tr._L.mpx_gate(sp, 300.0)
+        e0.record(stream)
+        for i in range(10):
+            full.g_jac_dev(z_d[0].data_ptr(), p_d.data_ptr(), g_ref.data_ptr(), v_ref.data_ptr(), sp)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_single = e0.elapsed_time(e1) / 10
+
+        def verify(g_t, v_t, f_t=None, grad_t=None):
+            """Every rank's gathered buffers against the single-GPU evaluation of the whole NLP: g and the Jacobian
+            values bit for bit; f and grad_f (partials summed in another order) to 1e-12."""
+            ok = torch.equal(g_ref, g_t) and torch.equal(v_ref, v_t)
+            if f_t is not None:
+                ok = ok and bool(abs(float(f_t[0]) - float(f_ref[0])) <= 1e-12 * max(1.0, abs(float(f_ref[0]))))
+                ok = ok and bool(torch.max(torch.abs(grad_t - grad_ref) / torch.clamp(torch.abs(grad_ref), min=1.0)) <= 1e-12)
+            okt = torch.tensor([int(ok)], device=dev)
             dist.all_reduce(okt, op=dist.ReduceOp.MIN)
             return bool(okt.item())
 
         ng = max(3, min(args.steps, 20))
-        recv = 8 * (world - 1) * own  # bytes every rank receives per evaluation
+        recv = 8 * (world - 1) * own  # bytes every rank receives per evaluation (g + Jacobian values of the other shards)
+        og = sh.ObjectiveGatherer(tr.layout, part, dist, rank)
+        f_t = torch.zeros(1, dtype=torch.float64, device=dev)
+        grad_t = torch.empty(n_z, dtype=torch.float64, device=dev)
+
+        def objective(k):  # objective partials + grad_f shards: one all-reduce of a few doubles, one all-gather
+            tr.f_grad_dev(z_d[k].data_ptr(), p_d.data_ptr(), f_t.data_ptr(), grad_t.data_ptr(), sp)
+            og.all_gather(f_t, grad_t)
+
+        common = {"bytes_received_per_rank": int(recv), "nvlink_peer_copy_gbs": 770.0,
+                  "ingress_floor_ms": recv / 770e9 * 1e3, "single_gpu_same_nlp_ms": ms_single,
+                  "note": "every rank ends with the whole g / Jacobian / grad_f; NVLink (0.77 TB/s) is 8x slower than HBM, "
+                          "so this can never beat evaluating the whole NLP on one GPU (single_gpu_same_nlp_ms) -- "
+                          "SURVEY.md 8e; it is the north-star's exchange, measured, not the recommended mode"}
         # (a) fused peer stores
         pb = sh.PeerBuffers(n_g, nnz, dist, rank, local, n_sets=R)
         flag = torch.zeros(1, device=dev)
 
-        def fstep(i):
+        def fstep(i, with_obj=True):
             k = i % R
             g_t, v_t = pb.local(k)
             pg, pv = pb.peers(k)
             tr.g_jac_dev_peers(z_d[k].data_ptr(), p_d.data_ptr(), g_t.data_ptr(), v_t.data_ptr(), pg, pv, sp)
-            dist.all_reduce(flag)  # every rank's kernel (and with it its peer stores) has completed
+            if with_obj:
+                objective(k)
+            else:
+                dist.all_reduce(flag)  # every rank's kernel (and with it its peer stores) has completed
 
         for i in range(3):
             fstep(i)
         barrier()
         fstep(0)
-        torch.cuda.synchronize()
-        ok = verify(*pb.local(0)) if world <= 2 else None
         barrier()
-        e0.record(stream)
-        for i in range(ng):
-            fstep(i)
-        e1.record(stream)
-        barrier()
-        ms_f = max_over_ranks(e0.elapsed_time(e1)) / ng
-        allgather = {"value": world * 1e3 / ms_f, "unit": UNIT, "ms_per_step": ms_f, "steps": ng, "equals_single_gpu": ok,
-                     "bytes_sent_per_rank": int(recv), "nvlink_gbs_per_rank": recv / (ms_f * 1e-3) / 1e9,
+        ok = verify(*pb.local(0), f_t, grad_t)
+        res = {}
+        for name, with_obj in (("jacobian_only", False), ("with_objective", True)):
+            barrier()
+            e0.record(stream)
+            for i in range(ng):
+                fstep(i, with_obj)
+            e1.record(stream)
+            barrier()
+            res[name] = max_over_ranks(e0.elapsed_time(e1)) / ng
+        ms_f = res["with_objective"]
+        allgather = {"value": (1 if strong else world) * 1e3 / ms_f, "unit": UNIT, "ms_per_step": ms_f,
+                     "ms_per_step_jacobian_only": res["jacobian_only"], "steps": ng, "equals_single_gpu": ok,
+                     "nvlink_gbs_per_rank": recv / (res["jacobian_only"] * 1e-3) / 1e9, **common,
                      "how": "mpx_eval_g_jac_dev_peers: each image is handed to the copy engine once per destination "
-                            "(cp.async.bulk to peer-mapped memory), g by plain peer stores; + one 4-byte all-reduce"}
+                            "(cp.async.bulk to peer-mapped memory), g by plain peer stores; then f + grad_f of the shard, "
+                            "one all-reduce of the objective partials (which also orders the ranks) and one all-gather "
+                            "of the grad_f shards"}
         pb.close()
         # (b) NCCL baseline
         row0 = None
@@ -404,28 +460,35 @@ def run_cuda(args):
             row0 = lambda g, v: tr0.g_jac_dev(z_cur[0].data_ptr(), p_d.data_ptr(), g.data_ptr(), v.data_ptr(), sp)
         gather = sh.Gatherer(tr.layout, part, dist, rank, dev, row0)
 
-        def gstep(i):
+        def gstep(i, with_obj=True):
             k = i % R
             z_cur[0] = z_d[k]
             step(i)
             gather.all_gather(g_d[k], v_d[k])
+            if with_obj:
+                objective(k)
 
         for i in range(3):
             gstep(i)
         barrier()
         gstep(0)
-        torch.cuda.synchronize()
-        ok = verify(g_d[0], v_d[0]) if world <= 2 else None
         barrier()
-        e0.record(stream)
-        for i in range(ng):
-            gstep(i)
-        e1.record(stream)
-        barrier()
-        ms_g = max_over_ranks(e0.elapsed_time(e1)) / ng
-        allgather_nccl = {"value": world * 1e3 / ms_g, "unit": UNIT, "ms_per_step": ms_g, "steps": ng, "mode": gather.mode,
-                          "equals_single_gpu": ok, "bytes_received_per_rank": int(recv),
-                          "how": "shard kernel, then one NCCL all-gather of g / CSR values (torch.distributed)"}
+        ok = verify(g_d[0], v_d[0], f_t, grad_t)
+        for name, with_obj in (("jacobian_only", False), ("with_objective", True)):
+            barrier()
+            e0.record(stream)
+            for i in range(ng):
+                gstep(i, with_obj)
+            e1.record(stream)
+            barrier()
+            res[name] = max_over_ranks(e0.elapsed_time(e1)) / ng
+        ms_g = res["with_objective"]
+        allgather_nccl = {"value": (1 if strong else world) * 1e3 / ms_g, "unit": UNIT, "ms_per_step": ms_g,
+                          "ms_per_step_jacobian_only": res["jacobian_only"], "steps": ng, "mode": gather.mode,
+                          "equals_single_gpu": ok, **common,
+                          "how": "shard kernel, then one NCCL all-gather of g / CSR values (torch.distributed), then the "
+                                 "objective partials and grad_f shards the same way"}
+        del full, g_ref, v_ref, grad_ref
 
     # ---- end-to-end: host buffers through the C ABI (pinned); H2D of this rank's z / p and D2H of the rows it owns
     #      inside the timing.  Every rank uses its own PCIe link; no rank waits for another inside the timed region.
@@ -445,10 +508,74 @@ def run_cuda(args):
     dt = max_over_ranks(time.perf_counter() - t0) / n_e2e
     d2h = 8 * (n_g + nnz) if world == 1 else 8 * own
     h2d = 8 * (n_z + n_p) if world == 1 else 8 * ((K * deg + 1 + deg) * (tr.nx + tr.nu) + 2 + tr.na + n_p)
-    e2e = {"value": world / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+    e2e = {"value": (1 if strong else world) / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "ms_per_step": dt * 1e3, "steps": n_e2e,
            "api": "mpx_eval_jac_g (host pointers, pinned buffers)" + ("" if world == 1 else
                   "; per rank: its own shard over its own PCIe link, bytes are per rank")}
+    # ---- the same end to end, other ways a caller can hand over its buffers (N = 1; reported beside `e2e`, never as
+    #      the roofline): plain pageable numpy arrays (what IPOPT / CasADi allocate), the caller's pageable arrays
+    #      registered once with mpx_host_register, the dynamic fetch into a registered array (only the z-dependent
+    #      entries cross PCIe after the first call), and the packed dynamic entries
+    e2e_variants = None
+    if world == 1 and not args.no_e2e_variants:
+        def timed(fn, n=n_e2e):
+            for _ in range(2):
+                fn(0)
+            t = time.perf_counter()
+            for i in range(n):
+                fn(i)
+            return (time.perf_counter() - t) / n
+
+        zp_, pp_ = z_h.copy(), p_h.copy()        # pageable inputs
+        gp_, vp_ = np.empty(n_g), np.empty(nnz)  # pageable outputs
+
+        def bump(i):
+            zp_[node0] = float(z_h[node0] + 1e-6 * i)
+
+        def full(i):
+            bump(i)
+            tr.jac_g_values(zp_, pp_, out=vp_, g_out=gp_)
+
+        e2e_variants = {}
+        dt_page = timed(full)
+        e2e_variants["pageable"] = {"value": 1.0 / dt_page, "ms_per_step": dt_page * 1e3, "d2h_bytes_per_step": int(d2h),
+                                    "api": "mpx_eval_jac_g, plain numpy arrays (driver-staged copies)"}
+        try:
+            for a in (zp_, gp_, vp_):
+                tr.host_register(a)
+            dt_reg = timed(full)
+            e2e_variants["registered"] = {"value": 1.0 / dt_reg, "ms_per_step": dt_reg * 1e3, "d2h_bytes_per_step": int(d2h),
+                                          "api": "mpx_eval_jac_g after mpx_host_register of the caller's arrays"}
+            n_dyn = len(tr.dynamic_positions())
+
+            def dyn(i):
+                bump(i)
+                tr.jac_g_values_dynamic(zp_, pp_, out=vp_, g_out=gp_)
+
+            dt_dyn = timed(dyn)
+            chk = tr.jac_g_values(zp_, pp_)  # the buffer still holds the whole Jacobian of the last point
+            e2e_variants["dynamic"] = {"value": 1.0 / dt_dyn, "ms_per_step": dt_dyn * 1e3,
+                                       "d2h_bytes_per_step": int(8 * (n_g + n_dyn)), "n_dynamic": int(n_dyn), "nnz": int(nnz),
+                                       "equals_full_fetch": bool(np.array_equal(chk, vp_)),
+                                       "api": "mpx_eval_jac_g_dynamic: kernel stores of the z-dependent entries into the "
+                                              "registered (mapped) caller array; constants stay from the first call"}
+            pk = torch.empty(n_dyn, dtype=torch.float64).pin_memory().numpy()
+
+            def packed(i):
+                bump(i)
+                tr.jac_g_packed(zp_, pp_, out=pk, g_out=gp_)
+
+            dt_pk = timed(packed)
+            e2e_variants["packed"] = {"value": 1.0 / dt_pk, "ms_per_step": dt_pk * 1e3,
+                                      "d2h_bytes_per_step": int(8 * (n_g + n_dyn)),
+                                      "api": "mpx_eval_jac_g_packed: dynamic entries gathered on the device, one copy into "
+                                             "pinned memory (the caller keeps the constants and scatters)"}
+        finally:
+            for a in (zp_, gp_, vp_):
+                try:
+                    tr.host_unregister(a)
+                except Exception:
+                    pass
     sampler.stop_flag = True
     sampler.join(timeout=1.0)
 
@@ -473,8 +600,8 @@ def run_cuda(args):
         traffic = traffic.get(args.config) if isinstance(traffic, dict) else (traffic if args.config == "headline" else None)
     cb = cpu_baseline(budget_s=args.cpu_budget) if (not args.no_cpu and world == 1) else None
     line = {
-        "metric": METRIC, "value": world * 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": (1 if strong else world) * 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD['name']}, n_segments={K} per GPU: one fused g + jac_g evaluation of {K} "
                                "segments per step and GPU",
@@ -483,8 +610,10 @@ def run_cuda(args):
                    "n_segments_total": Kt, "n_z": n_z, "n_g": n_g, "nnz_jac": nnz, "algorithmic_bytes_per_gpu": int(B),
                    "l2": f"{R} rotating z/g/values sets ({R * B / 1e6:.0f} MB written per GPU > 126 MB L2), launches back to back",
                    "parallelism": "1 GPU" if world == 1 else
-                   f"one NLP of {Kt} segments, {K} per GPU over {world} GPUs; rows stay on the GPU that computed them "
-                   f"(no data-path collective); value = {K}-segment evaluations per second summed over the GPUs",
+                   (f"one NLP of {Kt} segments split over {world} GPUs ({K} each); rows stay on the GPU that computed "
+                    f"them (no data-path collective); value = evaluations of the whole NLP per second" if strong else
+                    f"one NLP of {Kt} segments, {K} per GPU over {world} GPUs; rows stay on the GPU that computed them "
+                    f"(no data-path collective); value = {K}-segment evaluations per second summed over the GPUs"),
                    "program": tr.program_origin},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": f"mpx_gjac2_kernel<{WORKLOAD['problem']}, JAC, {deg if isinstance(deg, int) else 0}>",
@@ -495,6 +624,8 @@ def run_cuda(args):
                             "after a 256 MB read that evicts L2 (includes launch latency and a cold start)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
+    if e2e_variants is not None:
+        line["e2e_variants"] = e2e_variants
     if allgather is not None:
         line["allgather"] = allgather
         line["allgather_nccl"] = allgather_nccl
@@ -538,6 +669,8 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=25.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-allgather", action="store_true", help="N > 1: skip the extra all-gather measurement")
+    ap.add_argument("--no-e2e-variants", action="store_true", help="skip the pageable / registered / dynamic e2e legs")
+    ap.add_argument("--graph", action="store_true", help="time the K launches as one CUDA-graph launch (experiment)")
     ap.add_argument("--no-gate", action="store_true", help="do not enqueue the timed region behind a gate kernel")
     ap.add_argument("--config", default="headline", choices=sorted(WORKLOADS),
                     help="BASELINE.json configuration to time (default: the one the metric is quoted on)")

@@ -152,17 +152,20 @@ int mpx_eval_f_grad_dev(mpx_plan* plan, const double* d_z, const double* d_p, do
 int mpx_eval_g_jac_dev(mpx_plan* plan, const double* d_z, const double* d_p, double* d_g, double* d_values_or_null,
                        void* stream);
 int mpx_sync(mpx_plan* plan);
-/* -- the host hop. The reference's consumers (IPOPT through CasADi, mpopt.py:804) own host buffers, so every
+/* -- the host hop. The reference's consumers (IPOPT through CasADi, mpopt.py:804) own PAGEABLE host buffers, so every
  *    evaluation ends with a device-to-host copy that dwarfs the kernel (105 MB of Jacobian values at the headline
- *    size: 2 ms over PCIe 5 against a 19 us kernel). Two things help a caller whose buffers are stable:
- *    mpx_host_register pins a caller-owned range (cudaHostRegister, mapped) for the life of the plan or until
- *    mpx_host_unregister -- copies into it run at full link speed instead of through the driver's bounce buffers --
- *    and mpx_eval_jac_g_dynamic then moves only the n_dynamic entries that depend on z or p (the off-block partials,
- *    the merged D diagonals, d/dT0, d/dTF, path and terminal rows): the first call on a registered
- *    buffer is a full mpx_eval_jac_g, later ones rewrite just those entries in place. The caller must not modify
- *    `values` in between, and must unregister before freeing the memory. Unregistered `values`: plain full fetch.
- *    mpx_eval_jac_g_packed returns the dynamic entries packed (n_dynamic doubles, positions from
- *    mpx_jac_dynamic_positions, ascending CSR order) for callers that keep their own copy of the constants. */
+ *    size: 2 ms over PCIe 5 against a 19 us kernel).
+ *    - Every host-pointer entry point moves pageable buffers through a plan-owned pinned staging ring, copied in / out
+ *      by a small worker pool while the next chunk is in flight (link speed instead of the driver's bounce buffers);
+ *      MPX_HOST_THREADS sets the pool size. Pinned or registered buffers are used directly.
+ *    - mpx_host_register pins a caller-owned range (cudaHostRegister) for the life of the plan or until
+ *      mpx_host_unregister; the caller must unregister before freeing the memory.
+ *    - mpx_eval_jac_g_dynamic moves only the n_dynamic entries that depend on z or p (the off-block partials, the
+ *      merged D diagonals, d/dT0, d/dTF, path and terminal rows): the first call on a given `values`
+ *      buffer is a full mpx_eval_jac_g, later calls ON THE SAME BUFFER rewrite just those entries in place (packed
+ *      copy + parallel scatter). The caller must not modify `values` in between.
+ *    - mpx_eval_jac_g_packed returns the dynamic entries packed (n_dynamic doubles, positions from
+ *      mpx_jac_dynamic_positions, ascending CSR order) for callers that keep their own copy of the constants. */
 int mpx_host_register(mpx_plan* plan, void* ptr, int64_t bytes);
 int mpx_host_unregister(mpx_plan* plan, void* ptr);
 int mpx_jac_dynamic_count(mpx_plan* plan, int64_t* n_dynamic);

@@ -16,7 +16,13 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
 #include <memory>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -122,17 +128,7 @@ __global__ void mpx_compact_kernel(const double* __restrict__ full, const int64_
   if (i < n) out[i] = full[map[i]];
 }
 
-// dynamic fetch: copy only the z- / p-dependent Jacobian entries straight into the caller's (registered, mapped) host
-// buffer over PCIe; everything else in that buffer is constant and was written by an earlier full fetch
-__global__ void mpx_scatter_dyn_kernel(const double* __restrict__ vals, const int32_t* __restrict__ pos,
-                                       double* __restrict__ host_vals, int64_t n) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const int32_t e = pos[i];
-    host_vals[e] = vals[e];
-  }
-}
-// the same entries gathered into a contiguous device buffer (the variant that ships them with ONE device-to-host copy)
+// dynamic fetch: the z- / p-dependent Jacobian entries gathered into a contiguous device buffer (ONE device-to-host copy)
 __global__ void mpx_gather_dyn_kernel(const double* __restrict__ vals, const int32_t* __restrict__ pos,
                                       double* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -240,6 +236,85 @@ __global__ void __launch_bounds__(MPX_SCAN_THREADS) mpx_scan_widths_kernel(const
   }
 }
 
+// ------------------------------------------------------------------ host side of the host hop
+// A small persistent worker pool: parallel_for(n, fn) runs fn(i) for i in [0, n) on the workers and the caller.
+// Used to move bytes between plan-owned pinned staging and caller-owned PAGEABLE buffers at memory speed (one thread
+// copies ~10 GB/s; the PCIe link delivers 54 GB/s) and to scatter the packed dynamic Jacobian entries.
+class MpxPool {
+ public:
+  explicit MpxPool(int n) {
+    for (int t = 0; t < n; ++t) workers_.emplace_back([this] { loop(); });
+  }
+  ~MpxPool() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& w : workers_) w.join();
+  }
+  int size() const { return (int)workers_.size() + 1; }
+  void parallel_for(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    {
+      std::lock_guard<std::mutex> l(m_);
+      fn_ = &fn, next_ = 0, total_ = n, pending_ = n, ++epoch_;
+      epoch_a_.store(epoch_, std::memory_order_release);
+    }
+    cv_.notify_all();
+    run();
+    std::unique_lock<std::mutex> l(m_);
+    done_.wait(l, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      int i;
+      const std::function<void(int)>* f;
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (!fn_ || next_ >= total_) return;
+        i = next_++, f = fn_;
+      }
+      (*f)(i);
+      std::lock_guard<std::mutex> l(m_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    unsigned long seen = 0;
+    for (;;) {
+      // the chunks of one transfer arrive ~100 us apart: spin that long before sleeping on the condition variable
+      // (a wake-up through the futex costs about as much as copying a worker's share of a chunk)
+      const auto t0 = std::chrono::steady_clock::now();
+      bool got = false;
+      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(300)) {
+        if (epoch_a_.load(std::memory_order_acquire) != seen) {
+          got = true;
+          break;
+        }
+      }
+      {
+        std::unique_lock<std::mutex> l(m_);
+        if (!got) cv_.wait(l, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+      }
+      run();
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, total_ = 0, pending_ = 0;
+  unsigned long epoch_ = 0;
+  std::atomic<unsigned long> epoch_a_{0};
+  bool stop_ = false;
+};
+
 // ------------------------------------------------------------------ plan
 struct PhaseLayout {
   int nc = 0, ntc = 0;
@@ -340,13 +415,18 @@ struct mpx_plan {
   std::vector<int64_t> h_runs[3];  // shard plans: (offset, count) runs of g / values / grad_f written by this shard
   int staged = 0;                  // MPX_STAGE_* results currently valid in the device buffers (mpx_stage / mpx_fetch)
   DevBuf d_ccs_perm, d_ccs_vals;   // CCS order of the Jacobian values, built on first use
-  // host buffers the caller has registered (mpx_host_register): pinned + mapped, so that copies run at full PCIe speed
-  // and the dynamic fetch can write the z-dependent entries straight into them
-  struct HostReg { char* base; size_t bytes; char* dev; bool primed; };
+  // host buffers the caller has registered (mpx_host_register): pinned, so that copies run at full PCIe speed without
+  // the staging ring
+  struct HostReg { char* base; size_t bytes; bool primed; };
   std::vector<HostReg> regs;
   DevBuf d_dyn_pos, d_dyn_vals;    // positions (CSR order, int32) of the z- / p-dependent Jacobian entries; gathered values
   std::vector<int32_t> h_dyn_pos;
   int64_t n_dyn = -1;
+  const double* dyn_primed = nullptr;  // unregistered buffer that holds the constants (last full mpx_eval_jac_g_dynamic)
+  // pinned staging ring (MPX_STAGE_SLOTS x MPX_STAGE_BYTES) + worker pool for caller buffers that are pageable
+  std::unique_ptr<MpxPool> pool;
+  char* h_ring = nullptr;
+  cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf d_trace;                  // MPX_TRACE=1: timeline records of the K2 kernel (diagnostics), ring of MPX_TRACE_RING launches
   int64_t trace_seq = 0;
   const MpxProgramEntry* prog = nullptr;
@@ -357,6 +437,9 @@ struct mpx_plan {
   bool smem_too_big = false;
   ~mpx_plan() {
     for (auto& r : regs) cudaHostUnregister(r.base);
+    if (h_ring) cudaFreeHost(h_ring);
+    for (auto& e : ring_ev)
+      if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -1784,14 +1867,98 @@ static int launch_f_grad(mpx_plan& p, const double* d_z, const double* d_p, doub
   return MPX_OK;
 }
 
+#define MPX_STAGE_SLOTS 4
+#define MPX_STAGE_BYTES ((size_t)8 << 20)
+static int ensure_staging(mpx_plan& p) {
+  if (p.h_ring) return MPX_OK;
+  CUDA_TRY(cudaHostAlloc((void**)&p.h_ring, MPX_STAGE_SLOTS * MPX_STAGE_BYTES, cudaHostAllocDefault));
+  for (auto& e : p.ring_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  if (!p.pool) {
+    int n = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("MPX_HOST_THREADS")) n = atoi(e);
+    p.pool.reset(new MpxPool(std::max(0, std::min(n, 32) - 1)));
+  }
+  return MPX_OK;
+}
+// true when the driver can DMA straight from / into `ptr` (cudaHostAlloc'ed or registered memory)
+static bool is_pinned(const void* ptr) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+static void pool_memcpy(MpxPool& pool, char* dst, const char* src, size_t bytes) {
+  const int parts = (int)std::min<size_t>((size_t)pool.size(), (bytes + (256 << 10) - 1) / (256 << 10));
+  if (parts <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t step = ((bytes / parts) + 63) & ~(size_t)63;
+  pool.parallel_for(parts, [&](int i) {
+    const size_t a = (size_t)i * step, b = std::min(bytes, a + step);
+    if (a < b) memcpy(dst + a, src + a, b - a);
+  });
+}
+// device -> PAGEABLE host: chunks go through the pinned ring (DMA at link speed) and are copied out by the pool while
+// the next chunks are in flight.  `consume(slot_ptr, first_elem, n_elem)` handles a landed chunk (memcpy or scatter).
+static int staged_d2h(mpx_plan& p, const double* src, size_t n, const std::function<void(const double*, size_t, size_t)>& consume) {
+  int rc = ensure_staging(p);
+  if (rc) return rc;
+  const size_t per = MPX_STAGE_BYTES / sizeof(double), chunks = (n + per - 1) / per;
+  auto issue = [&](size_t c) -> cudaError_t {
+    const size_t a = c * per, cnt = std::min(per, n - a);
+    cudaError_t e = cudaMemcpyAsync(p.h_ring + (c % MPX_STAGE_SLOTS) * MPX_STAGE_BYTES, src + a, cnt * sizeof(double),
+                                    cudaMemcpyDeviceToHost, p.stream);
+    return e != cudaSuccess ? e : cudaEventRecord(p.ring_ev[c % MPX_STAGE_SLOTS], p.stream);
+  };
+  for (size_t c = 0; c < std::min<size_t>(chunks, MPX_STAGE_SLOTS - 1); ++c) CUDA_TRY(issue(c));
+  for (size_t c = 0; c < chunks; ++c) {
+    if (c + MPX_STAGE_SLOTS - 1 < chunks) CUDA_TRY(issue(c + MPX_STAGE_SLOTS - 1));  // its slot was consumed at c - 1
+    CUDA_TRY(cudaEventSynchronize(p.ring_ev[c % MPX_STAGE_SLOTS]));
+    const size_t a = c * per, cnt = std::min(per, n - a);
+    consume(reinterpret_cast<const double*>(p.h_ring + (c % MPX_STAGE_SLOTS) * MPX_STAGE_BYTES), a, cnt);
+  }
+  return MPX_OK;
+}
+static int d2h_any(mpx_plan& p, double* dst, const double* src, size_t n) {
+  if (n * sizeof(double) < ((size_t)1 << 20) || is_pinned(dst)) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
+    return MPX_OK;
+  }
+  return staged_d2h(p, src, n, [&](const double* s, size_t a, size_t cnt) {
+    pool_memcpy(*p.pool, (char*)(dst + a), (const char*)s, cnt * sizeof(double));
+  });
+}
+// PAGEABLE host -> device through the same ring
+static int h2d_any(mpx_plan& p, double* dst, const double* src, size_t n) {
+  if (n * sizeof(double) < ((size_t)1 << 20) || is_pinned(src)) {
+    CUDA_TRY(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+    return MPX_OK;
+  }
+  int rc = ensure_staging(p);
+  if (rc) return rc;
+  const size_t per = MPX_STAGE_BYTES / sizeof(double), chunks = (n + per - 1) / per;
+  for (size_t c = 0; c < chunks; ++c) {
+    const size_t a = c * per, cnt = std::min(per, n - a);
+    char* slot = p.h_ring + (c % MPX_STAGE_SLOTS) * MPX_STAGE_BYTES;
+    if (c >= MPX_STAGE_SLOTS) CUDA_TRY(cudaEventSynchronize(p.ring_ev[c % MPX_STAGE_SLOTS]));  // the slot's last DMA is done
+    pool_memcpy(*p.pool, slot, (const char*)(src + a), cnt * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(dst + a, slot, cnt * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+    CUDA_TRY(cudaEventRecord(p.ring_ev[c % MPX_STAGE_SLOTS], p.stream));
+  }
+  // a later staged transfer reuses the ring from slot 0: everything issued here has to be out of it first
+  for (size_t c = chunks > MPX_STAGE_SLOTS ? chunks - MPX_STAGE_SLOTS : 0; c < chunks; ++c)
+    CUDA_TRY(cudaEventSynchronize(p.ring_ev[c % MPX_STAGE_SLOTS]));
+  return MPX_OK;
+}
+
 // device -> host copy of a result vector: whole for a full plan, only the runs this shard writes for a shard plan
 // (the caller's array is full-size; other shards fill the rest -- each GPU moves its part over its own PCIe link)
 static int download(mpx_plan& p, int kind, double* dst, const double* src, size_t n_full) {
   const bool shard = p.seg_begin != 0 || p.seg_end != p.K;
-  if (!shard || (kind == 1 && !p.gather.empty())) {
-    CUDA_TRY(cudaMemcpyAsync(dst, src, n_full * sizeof(double), cudaMemcpyDeviceToHost, p.stream));
-    return MPX_OK;
-  }
+  if (!shard || (kind == 1 && !p.gather.empty())) return d2h_any(p, dst, src, n_full);
   std::vector<int64_t>& runs = p.h_runs[kind];
   if (runs.empty()) {
     int64_t n = 0;
@@ -1812,7 +1979,8 @@ static int upload_inputs(mpx_plan& p, const double* z, const double* pw) {
   CUDA_TRY(cudaSetDevice(p.device));
   p.staged = 0;  // every host entry point overwrites d_z (and then d_g / d_vals / d_f / d_grad): nothing staged survives
   if (p.seg_begin == 0 && p.seg_end == p.K) {
-    CUDA_TRY(cudaMemcpyAsync(p.d_z.p, z, (size_t)p.n_z * sizeof(double), cudaMemcpyHostToDevice, p.stream));
+    int rc = h2d_any(p, p.d_z.as<double>(), z, (size_t)p.n_z);
+    if (rc) return rc;
   } else {  // a shard reads only its own nodes (plus the node it shares with the previous segment) and t0 / tf / a
     // (one segment more at the end: the slope-continuity row of the last boundary reads the next segment's nodes)
     const int64_t nb = p.seg_start[p.seg_begin], cnt = p.seg_start[std::min(p.seg_end + 1, p.K)] - nb + 1, nv = p.nx + p.nu;
@@ -1867,14 +2035,8 @@ extern "C" int mpx_host_register(mpx_plan* p, void* ptr, int64_t bytes) {
   CUDA_TRY(cudaSetDevice(p->device));
   for (auto& r : p->regs)
     if (r.base == (char*)ptr && r.bytes == (size_t)bytes) return MPX_OK;
-  CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterMapped | cudaHostRegisterPortable));
-  void* dev = nullptr;
-  cudaError_t e = cudaHostGetDevicePointer(&dev, ptr, 0);
-  if (e != cudaSuccess) {
-    cudaHostUnregister(ptr);
-    return fail(MPX_ECUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e));
-  }
-  p->regs.push_back({(char*)ptr, (size_t)bytes, (char*)dev, false});
+  CUDA_TRY(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
+  p->regs.push_back({(char*)ptr, (size_t)bytes, false});
   return MPX_OK;
 }
 extern "C" int mpx_host_unregister(mpx_plan* p, void* ptr) {
@@ -1951,18 +2113,24 @@ extern "C" int mpx_jac_dynamic_positions(mpx_plan* p, int32_t* pos) {
   return MPX_OK;
 }
 
-// g + jac_g into caller-owned host buffers, moving only what changed: `values` must be a buffer registered with
-// mpx_host_register.  The first call on a registered buffer (and every call on an unregistered one) is a full
-// mpx_eval_jac_g, which also writes the constant entries; later calls evaluate on the device and store the n_dynamic
-// z- / p-dependent entries straight into the buffer (mapped host memory, PCIe writes from the kernel) -- 32 % of the
-// bytes at the headline size.  The caller must not modify `values` between calls (IPOPT does not).
+// g + jac_g into caller-owned host buffers, moving only what changed.  The first call on a given `values` buffer is a
+// full mpx_eval_jac_g, which also writes the constant entries; later calls on the SAME buffer evaluate on the device,
+// gather the n_dynamic z- / p-dependent entries (32 % of the bytes at the headline size), bring them over in chunks
+// through the pinned ring and scatter them into place with the worker pool while the next chunk is in flight.  (Storing
+// them from a kernel straight into mapped host memory was measured too: 2.07 ms against 2.12 ms for the full copy --
+// 40-byte PCIe writes -- so the packed copy + host scatter is what ships.)  The caller must not modify `values` between
+// calls (IPOPT does not).  Works with any host memory; registration only speeds up the first, full call.
 extern "C" int mpx_eval_jac_g_dynamic(mpx_plan* p, const double* z, const double* pw, double* g, double* values) {
   if (!p || !values) return fail(MPX_EINVAL, "NULL argument");
   const bool shard = p->seg_begin != 0 || p->seg_end != p->K;
-  mpx_plan::HostReg* reg = shard ? nullptr : find_reg(*p, values, (size_t)p->nnz * sizeof(double));
-  if (!reg || !reg->primed || p->adaptive) {
+  mpx_plan::HostReg* reg = find_reg(*p, values, (size_t)p->nnz * sizeof(double));
+  const bool primed = (reg && reg->primed) || p->dyn_primed == values;
+  if (shard || p->adaptive || !primed) {
     int rc = mpx_eval_jac_g(p, z, pw, g, values);
-    if (rc == MPX_OK && reg) reg->primed = true;
+    if (rc == MPX_OK && !shard && !p->adaptive) {
+      if (reg) reg->primed = true;
+      else p->dyn_primed = values;
+    }
     return rc;
   }
   int rc = build_dynamic(*p);
@@ -1971,21 +2139,31 @@ extern "C" int mpx_eval_jac_g_dynamic(mpx_plan* p, const double* z, const double
   if (rc) return rc;
   rc = launch_g_jac(*p, p->d_z.as<double>(), p->d_p.as<double>(), p->d_g.as<double>(), p->d_vals.as<double>(), p->stream);
   if (rc) return rc;
-  if (g && (rc = download(*p, 0, g, p->d_g.as<double>(), (size_t)p->n_g))) return rc;
+  CUDA_TRY(p->d_dyn_vals.ensure(std::max<int64_t>(p->n_dyn, 1) * sizeof(double)));
   if (p->n_dyn > 0) {
-    double* hv = reinterpret_cast<double*>(reg->dev + ((char*)values - reg->base));
-    mpx_scatter_dyn_kernel<<<(unsigned)((p->n_dyn + 255) / 256), 256, 0, p->stream>>>(p->d_vals.as<double>(),
-                                                                                   p->d_dyn_pos.as<int32_t>(), hv, p->n_dyn);
+    mpx_gather_dyn_kernel<<<(unsigned)((p->n_dyn + 255) / 256), 256, 0, p->stream>>>(p->d_vals.as<double>(),
+                                                                                  p->d_dyn_pos.as<int32_t>(),
+                                                                                  p->d_dyn_vals.as<double>(), p->n_dyn);
     CUDA_TRY(cudaGetLastError());
     ++p->launches;
+    const int32_t* pos = p->h_dyn_pos.data();
+    rc = staged_d2h(*p, p->d_dyn_vals.as<double>(), (size_t)p->n_dyn, [&](const double* src, size_t a, size_t cnt) {
+      const int parts = p->pool->size();
+      const size_t step = (cnt + parts - 1) / parts;
+      p->pool->parallel_for(parts, [&](int t) {
+        const size_t b = (size_t)t * step, e = std::min(cnt, b + step);
+        for (size_t i = b; i < e; ++i) values[pos[a + i]] = src[i];
+      });
+    });
+    if (rc) return rc;
   }
+  if (g && (rc = download(*p, 0, g, p->d_g.as<double>(), (size_t)p->n_g))) return rc;
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;
 }
 
-// variant B of the dynamic fetch (for comparison and for buffers that cannot be mapped): gather the dynamic entries
-// on the device, ONE contiguous device-to-host copy into plan-owned pinned memory; the caller scatters them with
-// mpx_jac_dynamic_positions (or keeps them packed).  packed: n_dynamic doubles.
+// the dynamic entries packed (n_dynamic doubles, order of mpx_jac_dynamic_positions), for callers that keep their own
+// copy of the constants or consume the entries in packed form
 extern "C" int mpx_eval_jac_g_packed(mpx_plan* p, const double* z, const double* pw, double* g, double* packed) {
   if (!p || !packed) return fail(MPX_EINVAL, "NULL argument");
   int rc = build_dynamic(*p);
@@ -2002,7 +2180,7 @@ extern "C" int mpx_eval_jac_g_packed(mpx_plan* p, const double* z, const double*
                                                                                   p->d_dyn_vals.as<double>(), p->n_dyn);
     CUDA_TRY(cudaGetLastError());
     ++p->launches;
-    CUDA_TRY(cudaMemcpyAsync(packed, p->d_dyn_vals.p, (size_t)p->n_dyn * sizeof(double), cudaMemcpyDeviceToHost, p->stream));
+    if ((rc = d2h_any(*p, packed, p->d_dyn_vals.as<double>(), (size_t)p->n_dyn))) return rc;
   }
   CUDA_TRY(cudaStreamSynchronize(p->stream));
   return MPX_OK;

@@ -150,6 +150,73 @@ class Gatherer:
             self._packed(g, vals)
 
 
+class ObjectiveGatherer:
+    """The objective side of the per-evaluation exchange: ``J`` partials and ``grad_f`` shards
+    (BASELINE.json north_star: "allgather of the per-shard CSR blocks and objective partials"; the objective is
+    ``J = Mayer + compW . vec(q)``, /root/reference/mpopt/mpopt.py:455).
+
+    A shard's ``f + grad_f`` evaluation (``Transcription.f_grad_dev`` of a plan created with ``segments=``) leaves in
+    a full-size gradient buffer (i) the node entries d J / d X(i, s), d J / d U(i, c) of the nodes it owns -- contiguous
+    runs, kind 2 of ``Layout.shard_runs`` -- and (ii) its PARTIAL sums of the entries every node contributes to,
+    d J / d t0, d J / d tf, d J / d a; the shard that holds the last segment adds the Mayer term, whose x0 entries land
+    on node 0's columns (owned by rank 0's shard).  So per evaluation:
+
+    * one all-reduce (sum) of ``[J, dJ/dt0, dJ/dtf, dJ/da (na), dJ/dx0 (nx)]`` per phase -- the partials;
+    * one all-gather of the kind-2 runs (packed) -- the shards.
+    """
+
+    def __init__(self, layout, part, dist, rank):
+        self.layout, self.part, self.dist, self.rank, self.world = layout, part, dist, rank, len(part)
+        self.runs = [layout.shard_runs(2, kb, ke) for kb, ke in part]
+        P, N, nx, nu, na = layout.P, layout.N, layout.nx, layout.nu, layout.na
+        nvar = layout.n_z // P
+        self.glob = []  # columns of the entries that are sums over shards, per phase: t0, tf, a.., x0..
+        for ph in range(P):
+            zo = ph * nvar
+            self.glob += [zo + (nx + nu) * N + j for j in range(2 + na)] + [zo + s * N for s in range(nx)]
+        self._send = self._recv = self._small = None
+
+    def all_gather(self, f, grad):
+        """``f``: 1-element tensor with this shard's partial objective, ``grad``: full-size gradient tensor holding
+        this shard's entries.  On return both are complete on every rank."""
+        import torch
+
+        if self.world == 1:
+            return
+        dist, idx = self.dist, torch.as_tensor(self.glob, device=grad.device)
+        # ---- partials: J and the entries summed over shards
+        small = torch.empty(1 + len(self.glob), dtype=grad.dtype, device=grad.device)
+        small[0] = f[0]
+        small[1:] = grad[idx]
+        nx = self.layout.nx
+        per = len(self.glob) // self.layout.P
+        own0, tail = self.part[self.rank][0] == 0, self.part[self.rank][1] == self.layout.K
+        if not (own0 or tail):  # neither the running-cost part (owner of node 0) nor the Mayer part (last shard)
+            for ph in range(self.layout.P):
+                small[1 + ph * per + per - nx:1 + (ph + 1) * per] = 0.0
+        dist.all_reduce(small)
+        # ---- shards: node entries of the gradient
+        lens = [sum(c for _, c in r) for r in self.runs]
+        mx = max(lens)
+        if self._send is None or self._send.device != grad.device:
+            self._send = torch.zeros(mx, dtype=grad.dtype, device=grad.device)
+            self._recv = torch.empty(mx * self.world, dtype=grad.dtype, device=grad.device)
+        torch.cat([grad[o:o + c] for o, c in self.runs[self.rank]], out=self._send[:lens[self.rank]])
+        dist.all_gather_into_tensor(self._recv, self._send)
+        dst, src = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            pos = r * mx
+            for o, c in self.runs[r]:
+                dst.append(grad[o:o + c])
+                src.append(self._recv[pos:pos + c])
+                pos += c
+        torch._foreach_copy_(dst, src)
+        f[0] = small[0]
+        grad[idx] = small[1:]
+
+
 class _DevArray:
     """A device allocation seen through ``__cuda_array_interface__`` (lets torch view memory it did not allocate)."""
 

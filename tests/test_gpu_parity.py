@@ -497,3 +497,125 @@ def test_reference_examples_run_time_compiled(libmpx, name, K, po, scheme):
     hrp, hci = tr.hess_structure()
     assert np.array_equal(hrp, H.indptr) and np.array_equal(hci, H.indices)
     assert_close(tr.hess_l_values(z, p, 0.7, lam), H.data, "hess_l values")
+
+
+# ----------------------------------------------------------------------------- host hop: registered buffers, dynamic fetch
+@pytest.mark.gpu
+@pytest.mark.parametrize("make,K,po,scheme", [
+    ("synthetic_6_3", 6, 5, "LGR"), ("kitchen_sink", 4, [3, 5, 4, 3], "LGR"), ("two_phase_schwartz", 3, 4, "LGL"),
+    ("moon_lander", 5, 4, "LGL"), ("delta3_launch_vehicle", 1, 5, "LGR")])
+def test_dynamic_fetch_equals_full_fetch(libmpx, make, K, po, scheme):
+    """mpx_eval_jac_g_dynamic into a registered buffer: first call = full fetch, later calls rewrite only the z- / p-
+    dependent entries -- and the buffer still equals a full evaluation at every new point.  The positions reported as
+    dynamic are exactly the entries that ever change."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle.nlp import OracleNLP
+
+    ocp = REGISTRY[make]()
+    tr = Transcription(ocp, K, po, scheme)
+    ora = OracleNLP(ocp, K, po, scheme)
+    z, w = random_point(ora, dirichlet=True)
+    vals, g = np.full(tr.nnz, np.nan), np.empty(tr.n_g)
+    tr.host_register(vals)
+    try:
+        pos = tr.dynamic_positions()
+        assert (np.diff(pos) > 0).all() and 0 < len(pos) < tr.nnz
+        full0 = tr.jac_g_values(z, w)
+        tr.jac_g_values_dynamic(z, w, out=vals, g_out=g)          # primes the buffer (full fetch)
+        assert np.array_equal(vals, full0)
+        changed = np.zeros(tr.nnz, bool)
+        rng = np.random.default_rng(5)
+        for it in range(3):
+            z2 = z + 0.05 * rng.standard_normal(z.size)
+            w2 = rng.dirichlet(np.ones(ora.K), size=ora.P).reshape(-1)
+            full = tr.jac_g_values(z2, w2)
+            before = vals.copy()
+            tr.jac_g_values_dynamic(z2, w2, out=vals, g_out=g)
+            assert np.array_equal(vals, full), f"dynamic fetch differs from the full fetch at point {it}"
+            assert_close(g, ora.g(z2, w2), "g of the dynamic fetch")
+            changed |= before != vals
+            packed = tr.jac_g_packed(z2, w2)
+            assert np.array_equal(packed, full[pos])
+        const = np.ones(tr.nnz, bool)
+        const[pos] = False
+        assert not changed[const].any(), "an entry outside the dynamic set changed"
+        assert_close(vals, ora.jac_g(z2, w2).data, "dynamic fetch vs oracle")
+    finally:
+        tr.host_unregister(vals)
+
+
+@pytest.mark.gpu
+def test_dynamic_fetch_tracks_the_buffer_it_primed(libmpx):
+    """Unregistered (pageable) buffers work too: the first call on a buffer writes everything, later calls on the SAME
+    buffer only the dynamic entries; handing in ANOTHER buffer is noticed and answered with a full fetch."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import moon_lander
+
+    tr = Transcription(moon_lander(), 4, 3, "LGR")
+    rng = np.random.default_rng(1)
+    z = rng.uniform(-1, 1, tr.n_z)
+    z[-2:] = [0.0, 3.0]
+    a, b = np.full(tr.nnz, np.nan), np.full(tr.nnz, np.nan)
+    tr.jac_g_values_dynamic(z, out=a)
+    assert np.array_equal(a, tr.jac_g_values(z))
+    z2 = z + 0.1
+    tr.jac_g_values_dynamic(z2, out=a)              # same buffer: dynamic entries only
+    assert np.array_equal(a, tr.jac_g_values(z2))
+    tr.jac_g_values_dynamic(z2, out=b)              # another buffer: everything
+    assert np.array_equal(b, a)
+    pos = tr.dynamic_positions()
+    b[pos] = np.nan
+    tr.jac_g_values_dynamic(z, out=b)               # b is primed now: its dynamic entries come back
+    assert np.array_equal(b, tr.jac_g_values(z))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make,K,po,world", [("kitchen_sink", 6, [3, 5, 4, 3, 2, 4], 3), ("moon_lander", 8, 3, 2),
+                                             ("synthetic_6_3", 6, 4, 3)])
+def test_sharded_objective_partials_sum_to_the_full_objective(libmpx, make, K, po, world):
+    """f + grad_f of shard plans (the objective side of the multi-GPU exchange): partial J and partial d/dt0, d/dtf,
+    d/da summed over the shards, node entries taken from their owners, Mayer x0 entries from the last shard --
+    exactly what mpopt_b200.shard.ObjectiveGatherer does with one all-reduce and one all-gather -- equal the
+    evaluation of the whole NLP."""
+    import torch
+
+    from mpopt_b200 import shard as sh
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle.nlp import OracleNLP
+
+    ocp = REGISTRY[make]()
+    ora = OracleNLP(ocp, K, po, "LGR")
+    z, w = random_point(ora, dirichlet=True)
+    pol = [po] * K if isinstance(po, int) else list(po)
+    part = sh.partition(pol, world)
+    dev = torch.device("cuda", 0)
+    zd, wd = torch.from_numpy(z).to(dev), torch.from_numpy(w).to(dev)
+    fs, grads, og = [], [], None
+    for r, seg in enumerate(part):
+        tr = Transcription(ocp, K, po, "LGR", segments=seg)
+        og = og or sh.ObjectiveGatherer(tr.layout, part, None, 0)
+        f = torch.zeros(1, dtype=torch.float64, device=dev)
+        grad = torch.full((tr.n_z,), float("nan"), dtype=torch.float64, device=dev)
+        tr.f_grad_dev(zd.data_ptr(), wd.data_ptr(), f.data_ptr(), grad.data_ptr())
+        torch.cuda.synchronize()
+        fs.append(float(f[0])), grads.append(grad.cpu().numpy())
+    glob = np.asarray(og.glob)
+    per, nx = len(glob) // ora.P, ora.nx
+    x0 = np.zeros(len(glob), bool)
+    for ph in range(ora.P):
+        x0[ph * per + per - nx:(ph + 1) * per] = True
+    total = np.full(ora.n_z, np.nan)
+    for r in range(world):
+        for off, cnt in og.runs[r]:
+            total[off:off + cnt] = grads[r][off:off + cnt]
+    small = np.zeros(len(glob))
+    for r, (kb, ke) in enumerate(part):
+        v = grads[r][glob].copy()
+        if not (kb == 0 or ke == K):
+            v[x0] = 0.0
+        small += v
+    total[glob] = small
+    assert abs(sum(fs) - ora.f(z, w)) <= 1e-10 * max(1.0, abs(ora.f(z, w)))
+    assert_close(total, ora.grad_f(z, w), "gathered grad_f")

@@ -57,6 +57,60 @@ def _worker(rank, world, port, problem, K, po, q):
         dist.destroy_process_group()
 
 
+def _objective_worker(rank, world, port, problem, K, po, q):
+    """Every rank holds its shard of grad_f (node entries of the nodes it owns) and partial sums of J and of the
+    entries all nodes contribute to; after ObjectiveGatherer.all_gather every rank holds the oracle's f and grad_f."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ora, lay, pol, z = _setup(problem, K, po)
+        f_full, grad_full = float(ora.f(z)), torch.from_numpy(ora.grad_f(z).copy())
+        part = sh.partition(pol, world)
+        og = sh.ObjectiveGatherer(lay, part, dist, rank)
+        grad = torch.full_like(grad_full, float("nan"))
+        for off, cnt in lay.shard_runs(2, *part[rank]):
+            grad[off:off + cnt] = grad_full[off:off + cnt]
+        # partial sums: a fixed, rank-dependent split of every summed entry that adds up to the full value
+        wts = torch.tensor([(r + 1.0) for r in range(world)], dtype=torch.float64)
+        share = float(wts[rank] / wts.sum())
+        idx = torch.as_tensor(og.glob)
+        nx, per = lay.nx, len(og.glob) // lay.P
+        x0 = torch.zeros(len(og.glob), dtype=torch.bool)
+        for ph in range(lay.P):
+            x0[ph * per + per - nx:(ph + 1) * per] = True
+        grad[idx[~x0]] = grad_full[idx[~x0]] * share
+        # x0 entries: the owner of node 0 holds the running-cost part, the last shard the Mayer part (here: a split)
+        own0, tail = part[rank][0] == 0, part[rank][1] == lay.K
+        if own0 and tail:
+            grad[idx[x0]] = grad_full[idx[x0]]
+        elif own0:
+            grad[idx[x0]] = 0.25 * grad_full[idx[x0]]
+        elif tail:
+            grad[idx[x0]] = 0.75 * grad_full[idx[x0]]
+        f = torch.tensor([f_full * share], dtype=torch.float64)
+        og.all_gather(f, grad)
+        ok = bool(torch.allclose(grad, grad_full, rtol=1e-14, atol=1e-14) and abs(float(f[0]) - f_full) <= 1e-13 * max(1, abs(f_full)))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("problem,K,po,world", [
+    ("moon_lander", 8, 3, 2), ("kitchen_sink", 5, [3, 4, 2, 6, 3], 3), ("two_phase_schwartz", 4, 3, 2)])
+def test_objective_partials_and_grad_shards_gather(problem, K, po, world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_objective_worker, args=(r, world, port, problem, K, po, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    res = sorted(q.get(timeout=5) for _ in range(world))
+    assert all(r[1] for r in res), res
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
