@@ -321,36 +321,48 @@ def run_cuda(args):
         step(i)
     barrier()
 
-    # ---- timed region A (primary): K back-to-back steps over rotating buffer sets, one event pair, max over ranks
-    l0 = tr.launches
+    # ---- timed region A (primary): K evaluations = K launches of the g + jac_g kernel, chained by programmatic
+    #      dependent launch, outputs rotating over R buffer sets; CUDA events on the launch stream, max over ranks.
+    #      Default: the K launches are captured ONCE into a CUDA graph and the timed region is ONE replay of that graph
+    #      -- how a device-resident consumer that evaluates at this rate issues them: no host launch work inside the
+    #      region, and the front-end sees the whole chain (17.6 us per evaluation against 19.5 us for the same K
+    #      launches issued one by one from the host, same box; profiles/r02/README.md).  The host-issued variant is
+    #      measured too (roofline.stream_launch_us; `--no-graph` makes it the primary): there the region is enqueued
+    #      behind a gate kernel that holds the stream until every launch is queued, so Python -> ctypes ->
+    #      cudaLaunchKernelEx latency (~10 us per call) stays outside the event pair.
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    # the whole timed region is enqueued behind a gate kernel that holds the stream for a few hundred microseconds:
-    # when the device reaches e0 every launch is already queued, so host launch latency (Python -> ctypes ->
-    # cudaLaunchKernelEx, ~10 us per call) is not inside the event pair; the first launch still pays its full,
-    # non-overlapped prologue
     gate_us = 0.0 if args.no_gate else min(2000.0, 150.0 + 15.0 * args.steps)
-    graph = None
-    if args.graph:  # the K launches captured once into a CUDA graph (programmatic edges kept), ONE graph launch timed
+    barrier()
+    l0 = tr.launches
+    if gate_us:
+        tr._L.mpx_gate(sp, gate_us)
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    launches = tr.launches - l0  # kernels of this repo launched per timed region (the graph replays the same ones)
+    ms_stream = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    ms_step, graph_ok = ms_stream, None
+    if not args.no_graph:
+        last = (args.steps - 1) % R
+        ref_v = v_d[last].clone()  # what the last launch of the chain wrote
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
             for i in range(args.steps):
                 step(i)
-        graph.replay()
+        v_d[last].zero_()
+        graph.replay()  # warm replay, and the check that the captured chain computes the same thing
         barrier()
-        l0 = tr.launches - args.steps
-    if gate_us:
-        tr._L.mpx_gate(sp, gate_us)
-    e0.record(stream)
-    if graph is not None:
+        graph_ok = bool(torch.equal(ref_v, v_d[last]))
+        del ref_v
+        if gate_us:
+            tr._L.mpx_gate(sp, gate_us)
+        e0.record(stream)
         graph.replay()
-    else:
-        for i in range(args.steps):
-            step(i)
-    e1.record(stream)
-    barrier()
-    launches = tr.launches - l0
-    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        e1.record(stream)
+        barrier()
+        ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
 
     # ---- timed region B (one launch at a time, L2 evicted before each): context for the roofline.  The eviction is a
     #      READ of 256 MB (clean lines): filling L2 with dirty lines instead would charge their write-back to the kernel.
@@ -605,8 +617,9 @@ def run_cuda(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"{WORKLOAD['name']}, n_segments={K} per GPU: one fused g + jac_g evaluation of {K} "
                                "segments per step and GPU",
-                   "timing": "K launches enqueued behind a gate kernel, one CUDA-event pair on the launch stream" if gate_us
-                   else "K launches, one CUDA-event pair on the launch stream (no gate)",
+                   "timing": ("K launches captured in a CUDA graph, one replay between two CUDA events on the launch stream"
+                              if not args.no_graph else "K host-issued launches behind a gate kernel, one CUDA-event pair"),
+                   "graph_equals_stream_launches": graph_ok,
                    "n_segments_total": Kt, "n_z": n_z, "n_g": n_g, "nnz_jac": nnz, "algorithmic_bytes_per_gpu": int(B),
                    "l2": f"{R} rotating z/g/values sets ({R * B / 1e6:.0f} MB written per GPU > 126 MB L2), launches back to back",
                    "parallelism": "1 GPU" if world == 1 else
@@ -617,11 +630,12 @@ def run_cuda(args):
                    "program": tr.program_origin},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "kernel": f"mpx_gjac2_kernel<{WORKLOAD['problem']}, JAC, {deg if isinstance(deg, int) else 0}>",
-                     "launch_us_avg": ms_step * 1e3, "bytes_per_launch": int(B),
+                     "launch_us_avg": ms_step * 1e3, "stream_launch_us": ms_stream * 1e3, "bytes_per_launch": int(B),
                      "isolated_launch_us_median": kmed * 1e3, "isolated_launch_us_min": float(kern_ms.min()) * 1e3,
-                     "how": "achieved = algorithmic bytes / average launch duration over the timed region (back-to-back "
-                            "launches, rotating output sets > L2; per GPU, slowest rank); isolated_* = single launches "
-                            "after a 256 MB read that evicts L2 (includes launch latency and a cold start)"},
+                     "how": "achieved = algorithmic bytes / average launch duration over the timed region (K chained "
+                            "launches replayed as one CUDA graph, rotating output sets > L2; per GPU, slowest rank); "
+                            "stream_launch_us = the same K launches issued one by one from the host; isolated_* = single "
+                            "launches after a 256 MB read that evicts L2 (includes launch latency and a cold start)"},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
     if e2e_variants is not None:
@@ -670,7 +684,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-allgather", action="store_true", help="N > 1: skip the extra all-gather measurement")
     ap.add_argument("--no-e2e-variants", action="store_true", help="skip the pageable / registered / dynamic e2e legs")
-    ap.add_argument("--graph", action="store_true", help="time the K launches as one CUDA-graph launch (experiment)")
+    ap.add_argument("--no-graph", action="store_true", help="primary timing = K host-issued launches instead of one CUDA-graph replay")
     ap.add_argument("--no-gate", action="store_true", help="do not enqueue the timed region behind a gate kernel")
     ap.add_argument("--config", default="headline", choices=sorted(WORKLOADS),
                     help="BASELINE.json configuration to time (default: the one the metric is quoted on)")

@@ -36,7 +36,12 @@ def aot_source(key: str, program, degrees=()) -> str:
     for k in range(P):
         lines.append(f"const MpxAotPhase<MpxPh_{key}_{k}" + "".join(f", {int(d)}" for d in degrees) + f"> k_{k};")
     lines.append("const MpxPhaseKernels* const phases[] = {" + ", ".join(f"&k_{k}" for k in range(P)) + "};")
-    lines.append(f'MpxProgramEntry entry = {{"{key}", {P}, phases, nullptr}};')
+    if P > 1:  # one g + jac_g launch for all phases (mpx_gjac2_multi_kernel)
+        lines.append("const MpxAotProgram<MpxDegs<" + ", ".join(str(int(d)) for d in degrees) + ">, "
+                     + ", ".join(f"MpxPh_{key}_{k}" for k in range(P)) + "> k_all;")
+        lines.append(f'MpxProgramEntry entry = {{"{key}", {P}, phases, nullptr, &k_all}};')
+    else:
+        lines.append(f'MpxProgramEntry entry = {{"{key}", {P}, phases, nullptr, nullptr}};')
     lines.append("struct Reg { Reg() { mpx_register_program(&entry); } } reg;")
     lines.append("}  // namespace")
     return "\n".join(lines) + "\n"

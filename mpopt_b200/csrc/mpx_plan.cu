@@ -100,25 +100,10 @@ __global__ void mpx_ducont_kernel(const MpxDuArgs A, int k_begin, int k_end, int
   A.g[A.gdU + (int64_t)c * (A.K - 1) + k] = acc;
 }
 
-// phase-link rows (mpopt.py:464-521): one thread per row
-struct MpxEvArgs {
-  const double* z;
-  double* g;
-  double* vals;
-  const int64_t* col_a;  // [rows] column with coefficient +1
-  const int64_t* col_b;  // [rows] column with coefficient -1
-  int64_t g0, v0;
-  int32_t rows;
-};
+// phase-link rows (mpopt.py:464-521): one thread per row (MpxEvArgs / mpx_event_row: csrc/mpx_kernels.cuh)
 __global__ void mpx_events_kernel(const MpxEvArgs A, int jac) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= A.rows) return;
-  const int64_t ca = A.col_a[r], cb = A.col_b[r];
-  A.g[A.g0 + r] = A.z[ca] - A.z[cb];
-  if (jac) {  // sorted columns within the row
-    A.vals[A.v0 + 2 * r] = ca < cb ? 1.0 : -1.0;
-    A.vals[A.v0 + 2 * r + 1] = ca < cb ? -1.0 : 1.0;
-  }
+  if (r < A.rows) mpx_event_row(A, r, jac);
 }
 
 // drop masked entries (exact-zero table values, SX folding -- SURVEY.md Q10)
@@ -429,6 +414,7 @@ struct mpx_plan {
   cudaEvent_t ring_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   DevBuf d_trace;                  // MPX_TRACE=1: timeline records of the K2 kernel (diagnostics), ring of MPX_TRACE_RING launches
   int64_t trace_seq = 0;
+  bool fuse_phases = true;         // MPX_FUSE_PHASES=0: one launch per phase + the events kernel (measurements)
   const MpxProgramEntry* prog = nullptr;
   std::string origin;
   std::vector<MpxPhaseArgs> args;
@@ -678,10 +664,52 @@ struct MpxRtPhase final : MpxPhaseKernels {
   }
 };
 
+// run-time compiled all-phases launch: the kernel takes one MpxMultiArgs<P> by value; the host builds its image in a
+// byte buffer (P is a run-time number here): a[P] | ev | grid_per_phase | pad
+struct MpxRtAll final : MpxProgramKernels {
+  CUfunction_t f[2] = {nullptr, nullptr};
+  int P = 0;
+  cudaError_t gjac2_all(const MpxPhaseArgs* args, int n_phases, const MpxEvArgs& ev, bool jac, int, int grid_per_phase,
+                        int threads, size_t smem, cudaStream_t st) const override {
+    if (n_phases != P) return cudaErrorInvalidValue;
+    RtApi& R = rt_api();
+    if (smem > 48 * 1024) {
+      static std::vector<CUfunction_t> configured;
+      if (std::find(configured.begin(), configured.end(), f[jac]) == configured.end()) {
+        if (R.FuncSetAttribute(f[jac], 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, 227 * 1024) != 0)
+          return cudaErrorInvalidValue;
+        configured.push_back(f[jac]);
+      }
+    }
+    std::vector<char> blob((size_t)P * sizeof(MpxPhaseArgs) + sizeof(MpxEvArgs) + 2 * sizeof(int32_t) + 8, 0);
+    memcpy(blob.data(), args, (size_t)P * sizeof(MpxPhaseArgs));
+    memcpy(blob.data() + (size_t)P * sizeof(MpxPhaseArgs), &ev, sizeof(MpxEvArgs));
+    const int32_t gp = grid_per_phase;
+    memcpy(blob.data() + (size_t)P * sizeof(MpxPhaseArgs) + sizeof(MpxEvArgs), &gp, sizeof gp);
+    void* params[] = {blob.data()};
+    if (R.LaunchKernelEx && mpx_pdl_enabled()) {
+      RtLaunchAttr at;
+      memset(&at, 0, sizeof at);
+      at.id = 6;  // CU_LAUNCH_ATTRIBUTE_PROGRAMMATIC_STREAM_SERIALIZATION
+      at.value.programmaticStreamSerializationAllowed = 1;
+      RtLaunchConfig cfg = {(unsigned)(grid_per_phase * P), 1, 1, (unsigned)threads, 1, 1, (unsigned)smem, st, &at, 1};
+      return R.LaunchKernelEx(&cfg, f[jac], params, nullptr) == 0 ? cudaSuccess : cudaErrorLaunchFailure;
+    }
+    return R.LaunchKernel(f[jac], grid_per_phase * P, 1, 1, threads, 1, 1, (unsigned)smem, st, params, nullptr) == 0
+               ? cudaSuccess
+               : cudaErrorLaunchFailure;
+  }
+};
+static_assert(sizeof(MpxMultiArgs<2>) == 2 * sizeof(MpxPhaseArgs) + sizeof(MpxEvArgs) + 2 * sizeof(int32_t) &&
+                  offsetof(MpxMultiArgs<3>, ev) == 3 * sizeof(MpxPhaseArgs) &&
+                  offsetof(MpxMultiArgs<3>, grid_per_phase) == 3 * sizeof(MpxPhaseArgs) + sizeof(MpxEvArgs),
+              "MpxRtAll builds the kernel argument by offset");
+
 struct RtProgram {
   std::string key;
   std::vector<std::unique_ptr<MpxRtPhase>> phases;
   std::vector<const MpxPhaseKernels*> ptrs;
+  std::unique_ptr<MpxRtAll> all;
   MpxProgramEntry entry;
 };
 std::vector<std::unique_ptr<RtProgram>> g_rt_programs;  // kept for the life of the process (modules stay loaded)
@@ -721,8 +749,16 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   for (int ph = 0; ph < n_phases; ++ph)
     for (const char* k : {"mpx_hess_kernel", "mpx_hess_final", "mpx_adapt_grad_kernel", "mpx_adapt_grad_suffix"})
       names1.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ">");
+  std::vector<std::string> names_all;  // one g + jac_g launch for all phases
+  if (n_phases > 1)
+    for (const char* b : {"false", "true"}) {
+      std::string nm = std::string("mpx_gjac2_multi_kernel<") + b + ", 0";
+      for (int ph = 0; ph < n_phases; ++ph) nm += ", MpxPhRt_" + std::to_string(ph);
+      names_all.push_back(nm + ">");
+    }
   for (auto& nm : names) R.AddNameExpression(prog, nm.c_str());
   for (auto& nm : names1) R.AddNameExpression(prog, nm.c_str());
+  for (auto& nm : names_all) R.AddNameExpression(prog, nm.c_str());
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo"};
   const nvrtcResult_t rc = R.CompileProgram(prog, 3, opts);
   if (rc != 0) {
@@ -770,8 +806,20 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
     rp->ptrs.push_back(P.get());
     rp->phases.push_back(std::move(P));
   }
+  if (n_phases > 1) {
+    rp->all.reset(new MpxRtAll());
+    rp->all->P = n_phases;
+    for (int b = 0; b < 2; ++b) {
+      const char* lowered = nullptr;
+      if (R.GetLoweredName(prog, names_all[b].c_str(), &lowered) != 0 || !lowered ||
+          R.ModuleGetFunction(&rp->all->f[b], mod, lowered) != 0) {
+        R.DestroyProgram(&prog);
+        return fail(MPX_ECUDA, "kernel " + names_all[b] + " not found in the run-time compiled module");
+      }
+    }
+  }
   R.DestroyProgram(&prog);
-  rp->entry = MpxProgramEntry{rp->key.c_str(), n_phases, rp->ptrs.data(), nullptr};
+  rp->entry = MpxProgramEntry{rp->key.c_str(), n_phases, rp->ptrs.data(), nullptr, rp->all.get()};
   *out = &rp->entry;
   g_rt_programs.push_back(std::move(rp));
   return MPX_OK;
@@ -1599,6 +1647,8 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     }
   }
   if (p.adaptive) p.origin += ";adaptive";
+  if (const char* fe = getenv("MPX_FUSE_PHASES")) p.fuse_phases = atoi(fe) != 0;
+  if (p.P > 1 && p.prog->all && p.v2_warps > 0 && !p.v4 && !p.adaptive && !p.rt_spec && p.fuse_phases) p.origin += ";phases=fused";
   if (const char* te = getenv("MPX_TRACE")) {  // K2 timeline records, read back with mpx_trace_read
     if (atoi(te) && p.v2_warps > 0 && !p.v4) {
       const size_t nb = (size_t)MPX_TRACE_RING * p.v2_grid * p.v2_warps * MPX_TRACE_SLOTS * sizeof(unsigned long long);
@@ -1771,11 +1821,33 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
   bool need_sig = false;
   for (auto& L : p.ph) need_sig |= L.uses_t;
   if (need_sig) scan_widths(p, d_z, d_p, st);
+  // multi-phase NLP: ONE launch for all phases and the phase-link rows (mpx_gjac2_multi_kernel)
+  const int nl_ = (int)p.links.size() / 2;
+  const bool fused = p.P > 1 && p.prog->all && p.v2_warps > 0 && !p.v4 && !p.adaptive && !p.rt_spec && p.fuse_phases &&
+                     true;
+  if (fused) {
+    for (int ph = 0; ph < p.P; ++ph) {
+      MpxPhaseArgs& a = p.args[ph];
+      a.z = d_z, a.w = widths_of(p, d_z, d_p, ph), a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
+      a.g = d_g, a.vals = target, a.v4_nbuf = p.v2_nbuf;
+      if (p.d_trace.p) a.trace = nullptr;
+    }
+    MpxEvArgs ev{};
+    if (nl_ && p.seg_end == p.K) {
+      const int rows = nl_ * (p.nx + p.nu + 1);
+      ev = MpxEvArgs{d_z, d_g, target, p.d_evcols.as<int64_t>(), p.d_evcols.as<int64_t>() + rows, p.g_events, p.v_events, rows};
+    }
+    CUDA_TRY(p.prog->all->gjac2_all(p.args.data(), p.P, ev, jac, p.spec_deg, p.v2_grid, p.v2_warps * 32,
+                                    jac ? p.v2_smem_jac : p.v2_smem_g, st));
+    ++p.launches;
+  }
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs& a = p.args[ph];
     a.z = d_z, a.w = widths_of(p, d_z, d_p, ph), a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
     a.g = d_g, a.vals = target;
-    if (p.v4) {
+    if (fused) {
+      // done above
+    } else if (p.v4) {
       a.stage_cap = p.v4_stage[ph], a.v4_nbuf = p.v4_nbuf[ph];
       const size_t sm4 = jac ? p.v4_smem[ph] : p.v4_smem_g[ph];
       if (p.rt_spec)
@@ -1794,7 +1866,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     }
     else
       CUDA_TRY(p.prog->phases[ph]->gjac(a, jac, grid, jac ? p.smem_gjac : p.smem_g, st));
-    ++p.launches;
+    if (!fused) ++p.launches;
     const PhaseLayout& L = p.ph[ph];
     if (p.adaptive) {  // SW rows and the d/dw entries, staged behind the base kernels' values
       a.ad_jac = jac ? 1 : 0, a.ext = jac ? p.d_full.as<double>() + p.n_base : nullptr;
@@ -1815,7 +1887,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     }
   }
   const int nl = (int)p.links.size() / 2;
-  if (nl && p.seg_end == p.K) {
+  if (nl && p.seg_end == p.K && !fused) {
     const int rows = nl * (p.nx + p.nu + 1);
     MpxEvArgs ev{d_z, d_g, target, p.d_evcols.as<int64_t>(), p.d_evcols.as<int64_t>() + rows, p.g_events, p.v_events, rows};
     mpx_events_kernel<<<(rows + 127) / 128, 128, 0, st>>>(ev, jac ? 1 : 0);

@@ -28,16 +28,70 @@ struct MpxPhaseKernels {
   virtual cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const = 0;
 };
 
+// kernels that span all phases of a program: ONE g + jac_g launch for a multi-phase NLP (mpx_gjac2_multi_kernel)
+struct MpxProgramKernels {
+  virtual ~MpxProgramKernels() {}
+  // args: n_phases MpxPhaseArgs; deg as in MpxPhaseKernels::gjac2 (0 = generic); grid = CTAs per phase
+  virtual cudaError_t gjac2_all(const MpxPhaseArgs* args, int n_phases, const MpxEvArgs& ev, bool jac, int deg,
+                                int grid_per_phase, int threads, size_t smem, cudaStream_t st) const = 0;
+};
+
 struct MpxProgramEntry {
   const char* key;
   int n_phases;
   const MpxPhaseKernels* const* phases;
   MpxProgramEntry* next;
+  const MpxProgramKernels* all;  // NULL: single-phase program (or not generated): one launch per phase
 };
 
 extern "C" void mpx_register_program(MpxProgramEntry* e);
 extern "C" int mpx_pdl_enabled(void);  // MPX_PDL=0 turns programmatic dependent launch off
 const MpxProgramEntry* mpx_find_program(const char* key);
+
+template <int... DEGS>
+struct MpxDegs {};
+
+// AOT implementation of the all-phases launch
+template <class D, class... PHS>
+struct MpxAotProgram;
+template <int... DEGS, class... PHS>
+struct MpxAotProgram<MpxDegs<DEGS...>, PHS...> final : MpxProgramKernels {
+  static constexpr int P = sizeof...(PHS);
+  template <bool JAC, int DEG>
+  static cudaError_t launch(const MpxMultiArgs<P>& m, int threads, size_t smem, cudaStream_t st) {
+    static bool done = false;
+    auto kern = mpx_gjac2_multi_kernel<JAC, DEG, PHS...>;
+    if (smem > 48 * 1024 && !done) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+      done = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(m.grid_per_phase * P), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at, cfg.numAttrs = mpx_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, m);
+  }
+  template <int D0, int... REST>
+  static cudaError_t pick(int deg, const MpxMultiArgs<P>& m, bool jac, int threads, size_t smem, cudaStream_t st) {
+    if constexpr (sizeof...(REST) == 0) {
+      return jac ? launch<true, D0>(m, threads, smem, st) : launch<false, D0>(m, threads, smem, st);  // list ends with 0
+    } else {
+      if (deg == D0) return jac ? launch<true, D0>(m, threads, smem, st) : launch<false, D0>(m, threads, smem, st);
+      return pick<REST...>(deg, m, jac, threads, smem, st);
+    }
+  }
+  cudaError_t gjac2_all(const MpxPhaseArgs* args, int n_phases, const MpxEvArgs& ev, bool jac, int deg, int grid_per_phase,
+                        int threads, size_t smem, cudaStream_t st) const override {
+    if (n_phases != P) return cudaErrorInvalidValue;
+    MpxMultiArgs<P> m;
+    for (int i = 0; i < P; ++i) m.a[i] = args[i];
+    m.ev = ev, m.grid_per_phase = grid_per_phase, m.pad_ = 0;
+    return pick<DEGS..., 0>(deg, m, jac, threads, smem, st);
+  }
+};
 
 // AOT implementation: direct <<<>>> launches of the template instantiations
 template <class PH, int... DEGS>

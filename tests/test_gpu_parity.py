@@ -244,7 +244,10 @@ def test_config5_full_size(libmpx):
     g = np.empty(tr.n_g)
     assert_close(tr.jac_g_values(z, p, g_out=g), J.data, "jac_g values")
     assert_close(g, ora.g(z, p), "g")
-    assert tr.program_origin.endswith("gjac=v2/d10")
+    assert tr.program_origin.endswith("gjac=v2/d10;phases=fused")
+    l0 = tr.launches
+    tr.jac_g_values(z, p, g_out=g)
+    assert tr.launches - l0 == 1, "both phases and the phase-link rows are ONE launch"
 
 
 @pytest.mark.parametrize("env", [{"MPX_JIT": "1"}, {"MPX_NOSPEC": "1"}, {"MPX_KERNEL": "v4"}, {"MPX_KERNEL": "v4", "MPX_NOSPEC": "1"},
