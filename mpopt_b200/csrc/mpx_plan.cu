@@ -275,7 +275,7 @@ class MpxPool {
       // (a wake-up through the futex costs about as much as copying a worker's share of a chunk)
       const auto t0 = std::chrono::steady_clock::now();
       bool got = false;
-      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(300)) {
+      while (std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(150)) {
         if (epoch_a_.load(std::memory_order_acquire) != seen) {
           got = true;
           break;
@@ -1946,9 +1946,10 @@ static int ensure_staging(mpx_plan& p) {
   CUDA_TRY(cudaHostAlloc((void**)&p.h_ring, MPX_STAGE_SLOTS * MPX_STAGE_BYTES, cudaHostAllocDefault));
   for (auto& e : p.ring_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   if (!p.pool) {
-    int n = (int)std::thread::hardware_concurrency();
+    // copies and scatters are memory-bound: eight threads saturate a socket, more only fight the caller's own threads
+    int n = std::min(8, std::max(1, (int)std::thread::hardware_concurrency() / 2));
     if (const char* e = getenv("MPX_HOST_THREADS")) n = atoi(e);
-    p.pool.reset(new MpxPool(std::max(0, std::min(n, 32) - 1)));
+    p.pool.reset(new MpxPool(std::max(0, std::min(n, 64) - 1)));
   }
   return MPX_OK;
 }

@@ -36,7 +36,7 @@ calls = {
     "g + jac_g (mpx_eval_g_jac_dev)": (lambda: tr.g_jac_dev(zd.data_ptr(), pd.data_ptr(), g.data_ptr(), v.data_ptr(), sp), 8 * (tr.n_z + tr.n_p + tr.n_g + tr.nnz)),
     "g only": (lambda: tr.g_jac_dev(zd.data_ptr(), pd.data_ptr(), g.data_ptr(), None, sp), 8 * (tr.n_z + tr.n_p + tr.n_g)),
     "f + grad_f (mpx_eval_f_grad_dev)": (lambda: tr.f_grad_dev(zd.data_ptr(), pd.data_ptr(), f.data_ptr(), grad.data_ptr(), sp), 8 * (2 * tr.n_z + tr.n_p)),
-    "hess_l (mpx_eval_hess_l_dev)": (lambda: _lib.check(L.mpx_eval_hess_l_dev(tr._plan, zd.data_ptr(), pd.data_ptr(), C.c_double(0.7), lam.data_ptr(), hv.data_ptr(), sp)), 8 * (tr.n_z + tr.n_p + tr.n_g + 2 * nh)),
+    "hess_l (mpx_eval_hess_l_dev)": (lambda: _lib.check(L.mpx_eval_hess_l_dev(tr._plan, zd.data_ptr(), pd.data_ptr(), C.c_double(0.7), lam.data_ptr(), hv.data_ptr(), sp)), 8 * (tr.n_z + tr.n_p + tr.n_g + nh)),  # z, p, multipliers read, every entry written once
 }
 for name, (fn, nbytes) in calls.items():
     for _ in range(5):
