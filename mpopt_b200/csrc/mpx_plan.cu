@@ -353,6 +353,8 @@ struct mpx_plan {
   int seg_begin, seg_end;
   bool drop, uniform;
   bool adaptive = false, mid_res = false;  // widths-as-variables NLP (mpopt.py:2877-3375)
+  bool wcol = false;         // adaptive: the base kernel writes the trailing d/dw_k column of the F rows (rows in place)
+  bool base_direct = false;  // adaptive: every CSR entry is written at its final position (no gather pass)
   int64_t n_base = 0, n_ext = 0;           // staged values: [base kernels | mpx_adapt_kernel]
   std::vector<int> dmid_off;               // per unique degree: record offset in h_dmid
   std::vector<double> h_dmid;              // D at the mid points, [d][d+1] per degree
@@ -973,7 +975,9 @@ static void build_structure(mpx_plan& p) {
         if (L.f_nz[s]) B.add(cT0), B.add(cTF);
         for (int m = 0; m < na; ++m)
           if (pat[nx + nu + m]) B.add(colA(m));
-        if (p.adaptive && L.f_nz[s]) {  // h_k = (tf - t0)/delta * w_k; t_i also moves with every earlier width
+        if (p.adaptive && L.f_nz[s] && p.wcol) {
+          B.add(colW(k));  // written by the base kernel, in place
+        } else if (p.adaptive && L.f_nz[s]) {  // h_k = (tf - t0)/delta * w_k; t_i also moves with every earlier width
           if (L.f_t[s])
             for (int m = 0; m <= k; ++m) B.add_ext(colW(m), L.eF[s] + (int64_t)i * K + m);
           else
@@ -1163,9 +1167,19 @@ static void build_structure(mpx_plan& p) {
       }
     }
     if (p.nnz > done) p.gather_runs.push_back(done), p.gather_runs.push_back(p.nnz - done);
-    bool any = false;
-    for (int64_t v : p.sw_direct) any |= v >= 0;
+    bool any = false, all_sw = true;
+    for (int64_t v : p.sw_direct) any |= v >= 0, all_sw = all_sw && v >= 0;
     if (!any) p.gather_runs.clear();
+    // every entry outside the in-place SW blocks already sits at its CSR position (single phase, width column written
+    // by the base kernel, nothing folded away): the base kernels write straight into the caller's array
+    p.base_direct = all_sw && any;
+    for (size_t i = 0; p.base_direct && i + 1 < p.gather_runs.size(); i += 2)
+      for (int64_t e = p.gather_runs[i]; e < p.gather_runs[i] + p.gather_runs[i + 1]; ++e)
+        if (p.gather[e] != e) {
+          p.base_direct = false;
+          break;
+        }
+    if (p.base_direct) p.gather_runs.clear();
   }
 }
 
@@ -1251,6 +1265,18 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     if (k + 1 < K) p.nnzS += p.po[k] + p.po[k + 1] + 1;
   }
   p.ph.resize(p.P);
+  // widths-as-variables NLP: when no dynamics row depends on t explicitly, every F row gains exactly ONE width column
+  // (its own segment's w_k, last in the row), which the persistent-warp kernel writes itself -- the rows then need no
+  // gather pass.  (With explicit time dependence the row is dense in all earlier widths: mpx_adapt_kernel + gather.)
+  if (p.adaptive) {
+    const char* fk = getenv("MPX_KERNEL");
+    const char* we = getenv("MPX_ADAPT_WCOL");
+    bool ok = !(fk && (strcmp(fk, "v1") == 0 || strcmp(fk, "v4") == 0)) && !(we && atoi(we) == 0);
+    for (int k = 0; k < p.K; ++k) ok = ok && p.po[k] <= 31;
+    for (int ph = 0; ph < p.P && ok; ++ph)
+      for (int s = 0; s < nx && d->phases[ph].f_t; ++s) ok = ok && !d->phases[ph].f_t[s];
+    p.wcol = ok;
+  }
   int64_t row = 0, val = 0;
   for (int ph = 0; ph < p.P; ++ph) {
     const mpx_phase_desc& q = d->phases[ph];
@@ -1275,7 +1301,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
       int n = 2 * L.f_nz[s];
       for (int v = 0; v < nv; ++v)
         if (v != s && L.pat_f[(size_t)s * nv + v]) ++n;
-      L.f_next[s] = n;
+      L.f_next[s] = n + ((p.wcol && L.f_nz[s]) ? 1 : 0);  // + the w_k column of the widths-as-variables NLP
       L.uses_t |= L.f_t[s] != 0;
     }
     for (int c = 0; c < L.nc; ++c) {
@@ -1299,8 +1325,8 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
       // ext section: what mpx_adapt_kernel writes, in its own regular layout
       int64_t e = p.n_ext;
       for (int s = 0; s < nx; ++s) {
-        L.eF[s] = L.f_nz[s] ? e : -1;
-        if (L.f_nz[s]) e += L.f_t[s] ? (int64_t)N * K : N;
+        L.eF[s] = (L.f_nz[s] && !p.wcol) ? e : -1;
+        if (L.f_nz[s] && !p.wcol) e += L.f_t[s] ? (int64_t)N * K : N;
       }
       for (int c = 0; c < L.nc; ++c) {
         L.eC[c] = L.c_t[c] ? e : -1;
@@ -1597,6 +1623,8 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     }
   }
 
+  if (p.wcol && (p.v2_warps == 0 || p.v4))
+    return fail(MPX_ELIMIT, "adaptive NLP: the in-place width column needs the persistent-warp kernel (set MPX_ADAPT_WCOL=0)");
   if (p.v2_warps == 0 && p.smem_too_big)
     return fail(MPX_ELIMIT, "segment too large for the shared-memory staged kernels (degree x states)");
   p.origin += p.v4 ? ";gjac=v4" : (p.v2_warps > 0 ? ";gjac=v2" : ";gjac=v1");
@@ -1636,6 +1664,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     a.st = p.st, a.delta = p.tau_max - p.tau_min, a.tau0 = p.tau_min;
     a.ist = 1.0 / a.st, a.idelta = 1.0 / a.delta;
     if (p.adaptive) {
+      a.ad_wcol = p.wcol ? 1 : 0;
       a.ad_sw_u = L.sw_u, a.ad_sw_x = L.sw_x, a.ad_res = p.mid_res;
       a.ad_img = p.adapt_img[ph];
       a.dmid = p.d_dmid.as<double>(), a.seg_dmid = p.d_seg_dmid.as<int32_t>();
@@ -1646,7 +1675,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
       a.wpart = p.d_wpart.as<double>();
     }
   }
-  if (p.adaptive) p.origin += ";adaptive";
+  if (p.adaptive) p.origin += p.base_direct ? ";adaptive/in-place" : ";adaptive";
   if (const char* fe = getenv("MPX_FUSE_PHASES")) p.fuse_phases = atoi(fe) != 0;
   if (p.P > 1 && p.prog->all && p.v2_warps > 0 && !p.v4 && !p.adaptive && !p.rt_spec && p.fuse_phases) p.origin += ";phases=fused";
   if (const char* te = getenv("MPX_TRACE")) {  // K2 timeline records, read back with mpx_trace_read
@@ -1816,7 +1845,7 @@ static void scan_widths(mpx_plan& p, const double* d_z, const double* d_p, cudaS
 
 static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, double* d_g, double* d_vals, cudaStream_t st) {
   const bool jac = d_vals != nullptr;
-  double* target = jac ? (p.gather.empty() ? d_vals : p.d_full.as<double>()) : nullptr;
+  double* target = jac ? ((p.gather.empty() || p.base_direct) ? d_vals : p.d_full.as<double>()) : nullptr;
   const int grid = p.seg_end - p.seg_begin;
   bool need_sig = false;
   for (auto& L : p.ph) need_sig |= L.uses_t;
@@ -1894,7 +1923,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     CUDA_TRY(cudaGetLastError());
     ++p.launches;
   }
-  if (jac && !p.gather.empty() && p.gather_runs.empty()) {
+  if (jac && !p.gather.empty() && p.gather_runs.empty() && !p.base_direct) {
     mpx_compact_kernel<<<(unsigned)((p.nnz + 255) / 256), 256, 0, st>>>(p.d_full.as<double>(), p.d_gather.as<int64_t>(),
                                                                        d_vals, p.nnz);
     CUDA_TRY(cudaGetLastError());

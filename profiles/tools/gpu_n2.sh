@@ -1,8 +1,19 @@
 #!/bin/bash
-# 2-GPU call: both bench arms under torchrun exactly as the driver launches them; stdout must be ONE JSON line
-TAG=${1:-n2}
-OUT=gpurun_out/$TAG
-mkdir -p $OUT
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 > $OUT/bench_n2.json 2> $OUT/bench_n2.err; echo "stdout lines: $(wc -l < $OUT/bench_n2.json)"; cut -c1-200 $OUT/bench_n2.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 > $OUT/bench_ref_n2.json 2> $OUT/bench_ref_n2.err; echo "stdout lines: $(wc -l < $OUT/bench_ref_n2.json)"; cut -c1-200 $OUT/bench_ref_n2.json
-timeout 300 python bench.py --no-cpu --steps 50 > $OUT/bench_n1.json 2> $OUT/bench_n1.err; echo "stdout lines: $(wc -l < $OUT/bench_n1.json)"; cut -c1-200 $OUT/bench_n1.json
+N=${1:-2}
+mkdir -p gpurun_out/n$N
+nvidia-smi topo -m > gpurun_out/n$N/topo.txt 2>&1; nproc >> gpurun_out/n$N/topo.txt; lscpu | grep -E "NUMA|Socket|Model name|^CPU\(s\)" >> gpurun_out/n$N/topo.txt
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/n$N/bench.json 2> gpurun_out/n$N/err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --config 4 --gpus $N --steps 20 --warmup 5 > gpurun_out/n$N/bench_c4.json 2>> gpurun_out/n$N/err
+tail -5 gpurun_out/n$N/err
+python - <<PY
+import json
+for f in ("bench","bench_c4"):
+    try:
+        d=json.load(open("gpurun_out/n$N/%s.json"%f))
+    except Exception as e:
+        print(f, "no json", e); continue
+    print(f, "value", round(d["value"],1), d["scaling"], "ms", round(d["ms_per_step"]*1e3,2), "frac", round(d["roofline"]["frac"],3), "e2e", round(d["e2e"]["value"],1))
+    for k in ("allgather","allgather_nccl"):
+        a=d.get(k)
+        if a: print("  ",k, {x:(round(v,3) if isinstance(v,float) else v) for x,v in a.items() if x not in ("how","note")})
+PY

@@ -61,7 +61,7 @@ def test_adaptive_nlp_matches_oracle(libmpx, name, problem, K, po, scheme, mid, 
             tabs[d] = (r, D, w, Cm)
     ora = OracleAdaptiveNLP(ocp, K, po, scheme, drop_exact_zeros=drop, mid_residuals=mid, tables=tabs)
     assert (tr.n_z, tr.n_p, tr.n_g) == (ora.n_z, 0, ora.n_g)
-    assert tr.program_origin.endswith(";adaptive")
+    assert tr.program_origin.split(";")[-1] in ("adaptive", "adaptive/in-place")
     z = _point(ora, problem)
     J = ora.jac_g(z)
     rp, ci = tr.structure()
@@ -229,3 +229,22 @@ def test_h_adaptive_width_update_two_phases(mp):
     ti, res = mpo.get_dynamics_residuals(sol)
     assert len(res) == 2 and len(res[0]) == 5
     assert abs(max(np.abs(r).max() for ph in res for r in ph if r is not None) - err) < 1e-12
+
+
+@pytest.mark.gpu
+def test_width_column_is_written_in_place(libmpx):
+    """Dynamics without explicit time dependence: the F rows carry ONE width column, written by the base kernel, so the
+    whole Jacobian lands at its CSR positions without a gather pass (2 launches: base kernel + mpx_adapt_kernel).
+    Time-dependent dynamics keep the staged path (rows dense in the earlier widths).  Both match the oracle (above)."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import kitchen_sink, moon_lander
+
+    tr = Transcription(moon_lander(), 6, 4, "LGR", adaptive=True)
+    assert tr.program_origin.endswith("adaptive/in-place")
+    rng = np.random.default_rng(0)
+    z = rng.uniform(0.1, 1.0, tr.n_z)
+    l0 = tr.launches
+    tr.jac_g_values(z)
+    assert tr.launches - l0 == 2
+    tr_t = Transcription(kitchen_sink(), 4, [3, 5, 4, 3], "LGR", adaptive=True)  # f depends on t
+    assert tr_t.program_origin.endswith(";adaptive")
