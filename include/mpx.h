@@ -70,6 +70,11 @@ typedef struct mpx_phase_desc {
   /* adaptive NLP only (mpx_problem_desc.adaptive): mid-point rows of the SW block, mpopt.py:3062-3082 */
   int32_t sw_u;            /* any control bound finite: compI.U rows present                */
   int32_t sw_x;            /* any state bound finite: compI.X rows present                  */
+  /* Hessian of the adaptive NLP (may be NULL / 0 otherwise): second-derivative pattern of sum_s mu_s f_s w.r.t.
+   * (x.., u.., a..), lower triangle, row-major [nv][nv] (the mid-point residual rows, mpopt.py:3084-3136), and whether
+   * the coefficient of h in the node Lagrangian, sw L - sum lamF Sx f, is not identically zero                        */
+  const uint8_t* pat_hf;
+  int32_t phi_nz;
 } mpx_phase_desc;
 
 typedef struct mpx_problem_desc {

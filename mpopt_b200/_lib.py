@@ -24,7 +24,7 @@ class PhaseDesc(C.Structure):
     _fields_ = [("n_path", C.c_int32), ("n_term", C.c_int32), ("pat_f", c_u8p), ("f_nz", c_u8p), ("f_t", c_u8p),
                 ("pat_c", c_u8p), ("c_t", c_u8p), ("pat_tc", c_u8p), ("diff_u", C.c_int32), ("midu", C.c_int32),
                 ("du_continuity", C.c_int32), ("cost_t", C.c_int32), ("pat_hw", c_u8p), ("pat_ht", c_u8p),
-                ("sw_u", C.c_int32), ("sw_x", C.c_int32)]
+                ("sw_u", C.c_int32), ("sw_x", C.c_int32), ("pat_hf", c_u8p), ("phi_nz", C.c_int32)]
 
 
 class ProblemDesc(C.Structure):

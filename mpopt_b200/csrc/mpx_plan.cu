@@ -305,7 +305,8 @@ struct PhaseLayout {
   int nc = 0, ntc = 0;
   bool has_DU = false, has_mU = false, has_dU = false;
   std::vector<int> f_next, c_len, tc_len;
-  std::vector<uint8_t> pat_f, f_nz, f_t, pat_c, c_t, pat_tc, pat_hw, pat_ht;
+  std::vector<uint8_t> pat_f, f_nz, f_t, pat_c, c_t, pat_tc, pat_hw, pat_ht, pat_hf;
+  bool phi_nz = false;
   bool has_hess = false;
   int64_t zoff = 0, n_g = 0;
   int64_t gF = 0, gC = 0, gDU = 0, gmU = 0, gdU = 0, gTC = 0;
@@ -398,6 +399,7 @@ struct mpx_plan {
   };
   std::vector<HessPhase> hess_ph;
   DevBuf d_node_seg, d_lam, d_hvals;
+  DevBuf d_hrowptr, d_hcolind, d_hpart2;  // adaptive NLP: Hessian pattern on the device, per-segment corner partials
   std::vector<int64_t> h_tail_runs[2];  // rows of the small tail kernels (mpx_eval_g_jac_dev_peers)
   std::vector<int64_t> h_runs[3];  // shard plans: (offset, count) runs of g / values / grad_f written by this shard
   int staged = 0;                  // MPX_STAGE_* results currently valid in the device buffers (mpx_stage / mpx_fetch)
@@ -610,7 +612,8 @@ struct MpxRtPhase final : MpxPhaseKernels {
   CUfunction_t f_gjac[2] = {nullptr, nullptr}, f_gjac2[2] = {nullptr, nullptr}, f_gjac4[2] = {nullptr, nullptr},
                f_fgrad[2] = {nullptr, nullptr}, f_final[2] = {nullptr, nullptr}, f_resid[2] = {nullptr, nullptr}, f_hess[2] = {nullptr, nullptr},
                f_adapt[3] = {nullptr, nullptr, nullptr},  // [0] unused, [1] adapt_grad, [2] suffix
-               f_adaptk[2] = {nullptr, nullptr};
+               f_adaptk[2] = {nullptr, nullptr}, f_ahess[2] = {nullptr, nullptr};
+  int nx_ = 0, nu_ = 0, na_ = 0;  // for the shared-memory bound of the adaptive Hessian kernel
   static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st,
                         bool pdl = false) {
     RtApi& R = rt_api();
@@ -664,6 +667,14 @@ struct MpxRtPhase final : MpxPhaseKernels {
     cudaError_t e = go(f_adapt[1], a, grid, MPX_THREADS, 0, st);
     return e != cudaSuccess || !suffix ? e : go(f_adapt[2], a, 1, 32, 0, st);
   }
+  cudaError_t adapt_hess(const MpxPhaseArgs& a, int grid, int dmax, cudaStream_t st) const override {
+    // the functor's NRG / NRH are not known on the host: bound them by the number of node variables
+    const int n1 = dmax + 1, ny = nx_ + nu_, nv = ny + na_, nr = 1 + nv + nv * (nv + 1) / 2;
+    const size_t dbl = 2 * (size_t)MpxTab::pad2(dmax * n1) + MpxTab::pad2(n1) + MpxTab::pad2(ny * n1) + MpxTab::pad2(ny * dmax) +
+                       MpxTab::pad2(dmax * nr) + MpxTab::pad2(n1 * (1 + nv)) + MpxTab::pad2(nx_ * dmax) + 4;
+    return go(f_ahess[0], a, grid, MPX_THREADS, dbl * sizeof(double), st);
+  }
+  cudaError_t adapt_hess_final(const MpxPhaseArgs& a, cudaStream_t st) const override { return go(f_ahess[1], a, 1, 64, 0, st); }
 };
 
 // run-time compiled all-phases launch: the kernel takes one MpxMultiArgs<P> by value; the host builds its image in a
@@ -726,7 +737,7 @@ std::string lib_dir() {
   return ".";
 }
 
-int compile_program(const char* key, const char* source, int n_phases, const MpxProgramEntry** out) {
+int compile_program(const char* key, const char* source, int n_phases, int nx, int nu, int na, const MpxProgramEntry** out) {
   RtApi& R = rt_api();
   if (!R.ok) return fail(MPX_ENOPROGRAM, "program '" + std::string(key) + "' is not compiled in and NVRTC is unavailable: " + R.err);
   const std::string hdr_path = lib_dir() + "/csrc/mpx_kernels.cuh";
@@ -749,7 +760,8 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
                         (strcmp(k, "mpx_gjac4_kernel") == 0 || strcmp(k, "mpx_gjac2_kernel") == 0 ? ", 0>" : ">"));
   std::vector<std::string> names1;  // kernels with the phase functor as their only template argument
   for (int ph = 0; ph < n_phases; ++ph)
-    for (const char* k : {"mpx_hess_kernel", "mpx_hess_final", "mpx_adapt_grad_kernel", "mpx_adapt_grad_suffix"})
+    for (const char* k : {"mpx_hess_kernel", "mpx_hess_final", "mpx_adapt_grad_kernel", "mpx_adapt_grad_suffix",
+                          "mpx_adapt_hess_kernel", "mpx_adapt_hess_final"})
       names1.push_back(std::string(k) + "<MpxPhRt_" + std::to_string(ph) + ">");
   std::vector<std::string> names_all;  // one g + jac_g launch for all phases
   if (n_phases > 1)
@@ -786,6 +798,7 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
   size_t idx = 0;
   for (int ph = 0; ph < n_phases; ++ph) {
     std::unique_ptr<MpxRtPhase> P(new MpxRtPhase());
+    P->nx_ = nx, P->nu_ = nu, P->na_ = na;
     CUfunction_t* slots[7] = {P->f_gjac, P->f_gjac2, P->f_gjac4, P->f_fgrad, P->f_final, P->f_resid, P->f_adaptk};
     for (int k = 0; k < 7; ++k)
       for (int b = 0; b < 2; ++b, ++idx) {
@@ -796,10 +809,10 @@ int compile_program(const char* key, const char* source, int n_phases, const Mpx
           return fail(MPX_ECUDA, "kernel " + names[idx] + " not found in the run-time compiled module");
         }
       }
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < 6; ++b) {
       const char* lowered = nullptr;
-      const std::string& nm = names1[(size_t)ph * 4 + b];
-      CUfunction_t* slot = b < 2 ? &P->f_hess[b] : &P->f_adapt[b - 1];
+      const std::string& nm = names1[(size_t)ph * 6 + b];
+      CUfunction_t* slot = b < 2 ? &P->f_hess[b] : (b < 4 ? &P->f_adapt[b - 1] : &P->f_ahess[b - 4]);
       if (R.GetLoweredName(prog, nm.c_str(), &lowered) != 0 || !lowered || R.ModuleGetFunction(slot, mod, lowered) != 0) {
         R.DestroyProgram(&prog);
         return fail(MPX_ECUDA, "kernel " + nm + " not found in the run-time compiled module");
@@ -1243,7 +1256,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
       if (!d->program_source)
         return fail(MPX_ENOPROGRAM, std::string("no compiled node functors registered for program key '") +
                                         d->program_key + "' and no program_source given");
-      int rc_ = compile_program(d->program_key, d->program_source, p.P, &p.prog);
+      int rc_ = compile_program(d->program_key, d->program_source, p.P, p.nx, p.nu, p.na, &p.prog);
       if (rc_) return rc_;
     }
   }
@@ -1292,6 +1305,8 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     L.has_hess = q.pat_hw != nullptr && q.pat_ht != nullptr;
     copy_pat(L.pat_hw, q.pat_hw, (size_t)(nv + 2) * (nv + 2));
     copy_pat(L.pat_ht, q.pat_ht, (size_t)(2 * nx + 2 + na) * (2 * nx + 2 + na));
+    copy_pat(L.pat_hf, q.pat_hf, (size_t)nv * nv);
+    L.phi_nz = q.phi_nz != 0;
     L.has_DU = q.diff_u != 0, L.has_mU = q.midu != 0, L.has_dU = q.du_continuity != 0 && K > 1;
     if (p.adaptive) L.has_mU = L.has_dU = false, L.sw_u = q.sw_u != 0, L.sw_x = q.sw_x != 0;  // rows [F C DU TC SW], :3169
     L.zoff = p.nvar * ph;
@@ -2319,9 +2334,15 @@ struct HessEntry { int a, b, cat, slot; };
 int build_hessian(mpx_plan& p) {
   if (p.hess_built) return MPX_OK;
   if (p.seg_begin != 0 || p.seg_end != p.K) return fail(MPX_EINVAL, "the Hessian needs a plan over all segments");
-  if (p.adaptive) return fail(MPX_EINVAL, "the Hessian of the adaptive NLP (widths as variables) is not implemented");
   for (auto& L : p.ph)
     if (!L.has_hess) return fail(MPX_ENOPROGRAM, "the problem description carries no Hessian patterns (pat_hw / pat_ht)");
+  if (p.adaptive)
+    for (auto& L : p.ph) {
+      if (L.uses_t || L.cost_t)
+        return fail(MPX_EINVAL, "the Hessian of the adaptive NLP is not available for problems with explicit time "
+                                "dependence (every earlier width moves t; use a quasi-Newton Hessian)");
+      if (L.pat_hf.empty()) return fail(MPX_ENOPROGRAM, "the problem description carries no pat_hf (adaptive Hessian)");
+    }
   const int nx = p.nx, nu = p.nu, na = p.na, ny = nx + nu, nv = ny + na, N = p.N, NW = nv + 2, NT = 2 * nx + 2 + na;
   const int it = nv, ih = nv + 1;
   std::vector<std::pair<int64_t, int64_t>> trip;
@@ -2391,6 +2412,62 @@ int build_hessian(mpx_plan& p) {
           const int64_t ca = termcol(L, a), cb = termcol(L, b);
           trip.emplace_back(std::max(ca, cb), std::min(ca, cb));
         }
+    if (p.adaptive) {  // what the widths add (mpx_adapt_hess_kernel): see the comment block there
+      auto colW = [&](int k) { return colT0(L) + 2 + na + k; };
+      std::vector<uint8_t> gy(nv, 0);  // psi = sum mu Sx f depends on node variable v
+      bool psi_nz = false;
+      for (int s = 0; s < nx; ++s) {
+        psi_nz |= L.f_nz[s] != 0;
+        for (int v = 0; v < nv; ++v) gy[v] |= L.pat_f[(size_t)s * nv + v];
+      }
+      for (int k = 0; k < p.K; ++k) {
+        const int s0 = p.seg_start[k], d = p.po[k], rb0 = k == 0 ? 0 : 1;
+        // (1) h_k bilinear in (T0 | TF, w_k)
+        for (int b = 0; b < ny; ++b)
+          if (L.pat_hw[(size_t)ih * NW + b])
+            for (int j = rb0; j <= d; ++j) trip.emplace_back(colW(k), colv(L, b, s0 + j));
+        for (int m = 0; m < na; ++m)
+          if (L.pat_hw[(size_t)ih * NW + ny + m]) trip.emplace_back(colW(k), colA(L, m));
+        if (L.phi_nz) trip.emplace_back(colW(k), colT0(L)), trip.emplace_back(colW(k), colT0(L) + 1);
+        if (!p.mid_res) continue;
+        // (2) mid-point residual rows
+        for (int b = 0; b < ny; ++b)
+          if (b < nx || gy[b])
+            for (int j = 0; j <= d; ++j) trip.emplace_back(colW(k), colv(L, b, s0 + j));
+        for (int b = 0; b < ny; ++b)
+          if (gy[b])
+            for (int j = 0; j <= d; ++j)
+              trip.emplace_back(colT0(L), colv(L, b, s0 + j)), trip.emplace_back(colT0(L) + 1, colv(L, b, s0 + j));
+        for (int m = 0; m < na; ++m)
+          if (gy[ny + m]) {
+            trip.emplace_back(colW(k), colA(L, m));
+            corner_on[ph][3 + 2 * m] = corner_on[ph][3 + 2 * m + 1] = 1;
+            trip.emplace_back(colA(L, m), colT0(L)), trip.emplace_back(colA(L, m), colT0(L) + 1);
+          }
+        if (psi_nz) {
+          trip.emplace_back(colW(k), colT0(L)), trip.emplace_back(colW(k), colT0(L) + 1);
+          trip.emplace_back(colW(k), colW(k));
+        }
+        for (int a = 0; a < nv; ++a)
+          for (int b = 0; b <= a; ++b) {
+            if (!L.pat_hf[(size_t)a * nv + b]) continue;
+            if (a < ny) {
+              for (int j = 0; j <= d; ++j)
+                for (int jp = 0; jp <= (a == b ? j : d); ++jp) trip.emplace_back(colv(L, a, s0 + j), colv(L, b, s0 + jp));
+            } else if (b < ny) {
+              for (int j = 0; j <= d; ++j) trip.emplace_back(colA(L, a - ny), colv(L, b, s0 + j));
+            } else {
+              const int c = 3 + 2 * na + (a - ny) * (a - ny + 1) / 2 + (b - ny);
+              if (!corner_on[ph][c]) {
+                corner_on[ph][c] = 1;
+                int64_t r, cc;
+                corner_cols(L, c, r, cc);
+                trip.emplace_back(r, cc);
+              }
+            }
+          }
+      }
+    }
   }
   std::sort(trip.begin(), trip.end());
   trip.erase(std::unique(trip.begin(), trip.end()), trip.end());
@@ -2472,6 +2549,13 @@ int build_hessian(mpx_plan& p) {
     H.blocks = (N + MPX_HESS_THREADS - 1) / MPX_HESS_THREADS, H.n_corner = n_corner;
     CUDA_TRY(H.part.ensure((size_t)H.blocks * n_corner * sizeof(double)));
   }
+  if (p.adaptive) {
+    CUDA_TRY(p.d_hrowptr.ensure(p.h_rowptr.size() * sizeof(int64_t)));
+    CUDA_TRY(p.d_hcolind.ensure(std::max<size_t>(p.h_colind.size(), 1) * sizeof(int64_t)));
+    CUDA_TRY(cudaMemcpy(p.d_hrowptr.p, p.h_rowptr.data(), p.h_rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(p.d_hcolind.p, p.h_colind.data(), p.h_colind.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(p.d_hpart2.ensure((size_t)p.K * (3 + 2 * na + na * (na + 1) / 2) * sizeof(double)));
+  }
   CUDA_TRY(p.d_lam.ensure((size_t)p.n_g * sizeof(double)));
   CUDA_TRY(p.d_hvals.ensure(p.h_colind.size() * sizeof(double)));
   p.hess_built = true;
@@ -2483,11 +2567,13 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
   bool need_sig = false;  // sigma only enters through explicit time dependence
   for (auto& L : p.ph) need_sig |= L.uses_t || L.cost_t;
   if (need_sig) scan_widths(p, d_z, d_p, st);
+  if (p.adaptive)  // the widths' contributions are ADDED on top of the node-local part (mpx_adapt_hess_kernel)
+    CUDA_TRY(cudaMemsetAsync(d_vals, 0, p.h_colind.size() * sizeof(double), st));
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs a = p.args[ph];
     auto& H = p.hess_ph[ph];
     a.ticket = p.d_ticket.p ? p.d_ticket.as<unsigned int>() + p.P + ph : nullptr;
-    a.z = d_z, a.w = d_p + (int64_t)ph * p.K, a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
+    a.z = d_z, a.w = widths_of(p, d_z, d_p, ph), a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
     a.lam = d_lam, a.lam_f = lam_f, a.node_seg = p.d_node_seg.as<int32_t>();
     a.hp_yy = H.pos_yy.as<int64_t>(), a.hp_ay = H.pos_ay.as<int64_t>(), a.hp_ty = H.pos_ty.as<int64_t>();
     a.hp_corner = H.pos_corner.as<int64_t>(), a.hp_term = H.pos_term.as<int64_t>();
@@ -2496,6 +2582,19 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
     a.hvals = d_vals, a.hpart = H.part.as<double>(), a.h_blocks = H.blocks;
     CUDA_TRY(p.prog->phases[ph]->hess(a, H.blocks, st));
     p.launches += a.ticket ? 1 : 2;
+    if (p.adaptive) {
+      a.h_rowptr = p.d_hrowptr.as<int64_t>(), a.h_colind = p.d_hcolind.as<int64_t>(), a.hpart2 = p.d_hpart2.as<double>();
+      const int dmax = *std::max_element(p.po.begin(), p.po.end());
+      for (int par = 0; par < 2; ++par) {
+        const int grid = (p.K - par + 1) / 2;
+        if (grid <= 0) continue;
+        a.ah_parity = par;
+        CUDA_TRY(p.prog->phases[ph]->adapt_hess(a, grid, dmax, st));
+        ++p.launches;
+      }
+      CUDA_TRY(p.prog->phases[ph]->adapt_hess_final(a, st));
+      ++p.launches;
+    }
   }
   return MPX_OK;
 }
@@ -2513,7 +2612,7 @@ extern "C" int mpx_hess_structure(mpx_plan* p, int64_t* nnz, int64_t* rowptr, in
 
 extern "C" int mpx_eval_hess_l_dev(mpx_plan* p, const double* d_z, const double* d_p, double lam_f, const double* d_lam_g,
                                    double* d_values, void* stream) {
-  if (!p || !d_z || !d_p || !d_lam_g || !d_values) return fail(MPX_EINVAL, "NULL argument");
+  if (!p || !d_z || (!d_p && p->n_p) || !d_lam_g || !d_values) return fail(MPX_EINVAL, "NULL argument");
   int rc = build_hessian(*p);
   if (rc) return rc;
   CUDA_TRY(cudaSetDevice(p->device));

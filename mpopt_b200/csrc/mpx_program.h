@@ -26,6 +26,9 @@ struct MpxPhaseKernels {
   // widths-as-variables NLP (mpopt_adaptive): extra rows / columns, and d f / d w
   virtual cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const = 0;
+  // Hessian of the widths-as-variables NLP: the part the widths add (one launch per segment parity, then the corner sum)
+  virtual cudaError_t adapt_hess(const MpxPhaseArgs& a, int grid, int dmax, cudaStream_t st) const = 0;
+  virtual cudaError_t adapt_hess_final(const MpxPhaseArgs& a, cudaStream_t st) const = 0;
 };
 
 // kernels that span all phases of a program: ONE g + jac_g launch for a multi-phase NLP (mpx_gjac2_multi_kernel)
@@ -221,6 +224,18 @@ struct MpxAotPhase final : MpxPhaseKernels {
   cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const override {
     mpx_adapt_grad_kernel<PH><<<grid, MPX_THREADS, 0, st>>>(a);
     if (suffix) mpx_adapt_grad_suffix<PH><<<1, 32, 0, st>>>(a);  // time-dependent running cost only
+    return cudaGetLastError();
+  }
+  cudaError_t adapt_hess(const MpxPhaseArgs& a, int grid, int dmax, cudaStream_t st) const override {
+    static bool done = false;
+    const size_t smem = (size_t)mpx_adapt_hess_smem_doubles<PH>(dmax) * sizeof(double);
+    cudaError_t e = allow_smem(mpx_adapt_hess_kernel<PH>, smem, done);
+    if (e != cudaSuccess) return e;
+    mpx_adapt_hess_kernel<PH><<<grid, MPX_THREADS, smem, st>>>(a);
+    return cudaGetLastError();
+  }
+  cudaError_t adapt_hess_final(const MpxPhaseArgs& a, cudaStream_t st) const override {
+    mpx_adapt_hess_final<PH><<<1, 64, 0, st>>>(a);
     return cudaGetLastError();
   }
 };

@@ -59,11 +59,13 @@ class Transcription:
             self.has_mU.append(mid and not self.adaptive)
             finite = lambda lo, hi: bool((np.asarray(lo) > -np.inf).any() or (np.asarray(hi) < np.inf).any())
             arrs = [_u8(pp.pat_f()), _u8(pp.f_nz), _u8(pp.f_t()), _u8(pp.pat_c()), _u8(pp.c_t()), _u8(pp.pat_tc()),
-                    _u8(pp.pat_hw()), _u8(pp.pat_ht())]
+                    _u8(pp.pat_hw()), _u8(pp.pat_ht()), _u8(pp.pat_hf())]
             self._keep += arrs
             d = phases[ph]
             d.n_path, d.n_term = pp.nc, pp.ntc
-            d.pat_f, d.f_nz, d.f_t, d.pat_c, d.c_t, d.pat_tc, d.pat_hw, d.pat_ht = [_lib.ptr(a, _lib.c_u8p) for a in arrs]
+            (d.pat_f, d.f_nz, d.f_t, d.pat_c, d.c_t, d.pat_tc, d.pat_hw, d.pat_ht,
+             d.pat_hf) = [_lib.ptr(a, _lib.c_u8p) for a in arrs]
+            d.phi_nz = int(bool(pp.L_nz) or any(pp.f_nz))
             d.diff_u, d.midu = int(bool(o.diff_u[ph])), int(mid and not self.adaptive)
             d.du_continuity = int(bool(o.du_continuity[ph]) and not self.adaptive)
             d.sw_u = int(self.adaptive and finite(o.lbu[ph], o.ubu[ph]))  # mpopt.py:3066-3068

@@ -92,6 +92,15 @@ class PhaseProgram:
             lag = tr.add(lag, tr.mul(self.lamC[q], self.c[q]))
         self.hess_vars = self.node_vars + [self.t, self.hs]
         self.hw = self._lower_hessian(lag, self.hess_vars)  # [(a, b, Expr)], b <= a
+        # ---- mid-point residual rows of the widths-as-variables NLP (mpopt.py:3084-3136): their Lagrangian term is
+        #      w_k sum_m (mu_m . DI X - h_k psi_m) with psi = sum_s mu_s Sx_s f_s evaluated at the interpolated mid
+        #      point; value, gradient and Hessian of psi w.r.t. (x.., u.., a..) (the multipliers ride in lamF)
+        psi = tr.as_expr(0.0)
+        for s in range(nx):
+            psi = tr.add(psi, tr.mul(tr.mul(self.lamF[s], self.sxs[s]), self.f[s]))
+        self.psi = psi
+        self.rg = [(v, d) for v, d in enumerate(tr.gradient(psi, self.node_vars)) if not d.is_value(0.0)]
+        self.rh = self._lower_hessian(psi, self.node_vars)
         self.lamT = [tr.var(f"{tag}lt{r}") for r in range(self.ntc)]
         theta = tr.mul(self.sw, self.M)
         for r in range(self.ntc):
@@ -114,6 +123,14 @@ class PhaseProgram:
         n = len(self.hess_vars)
         p = [[0] * n for _ in range(n)]
         for a, b, _ in self.hw:
+            p[a][b] = 1
+        return p
+
+    def pat_hf(self):
+        """[nv][nv] lower-triangle pattern of the second derivatives of sum_s mu_s f_s (residual rows, adaptive NLP)."""
+        n = self.nv
+        p = [[0] * n for _ in range(n)]
+        for a, b, _ in self.rh:
             p[a][b] = 1
         return p
 
@@ -379,6 +396,15 @@ class PhaseProgram:
         L += fn(f"hess_node({node_sig}, const double h, const double sw, const double* __restrict__ lf, "
                 f"const double* __restrict__ lc, const double* __restrict__ sxs, double* __restrict__ hw)",
                 [d for _, _, d in self.hw], [f"hw[{e}]" for e in range(len(self.hw))], ref, "w")
+        # value | gradient | Hessian of psi = sum_s lf_s sxs_s f_s  (mid-point residual rows of the adaptive NLP)
+        L.append(f"  static constexpr int NRG = {len(self.rg)}, NRH = {len(self.rh)};")
+        L.append(self._switch("rg_var", [v for v, _ in self.rg]))
+        L.append(self._switch("rh_a", [a for a, _, _ in self.rh]))
+        L.append(self._switch("rh_b", [b for _, b, _ in self.rh]))
+        L += fn(f"hess_res({node_sig}, const double* __restrict__ lf, const double* __restrict__ sxs, "
+                f"double* __restrict__ r)",
+                [self.psi] + [d for _, d in self.rg] + [d for _, _, d in self.rh],
+                [f"r[{e}]" for e in range(1 + len(self.rg) + len(self.rh))], ref, "r")
         ref = self._term_ref()
         ref[self.sw.name] = "sw"
         ref.update({v.name: f"lt[{i}]" for i, v in enumerate(self.lamT)})

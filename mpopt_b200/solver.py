@@ -48,7 +48,12 @@ class ScipyNlpSolver:
         fobj = lambda z: tr.f(z, p)
         fgrad = lambda z: tr.grad_f(z, p)
         eq = lbg == ubg
-        has_hess = not getattr(tr, "adaptive", False)
+        has_hess = True
+        if getattr(tr, "adaptive", False):  # the adaptive NLP has a Hessian kernel unless something depends on t
+            try:
+                tr.hess_structure()
+            except Exception:
+                has_hess = False
         n_ineq = int((~eq).sum())
         default = "ipm" if (has_hess and n_z + n_g + n_ineq <= 6000) else ("SLSQP" if n_z <= 600 else "trust-constr")
         method = self.options.get("method", default)
@@ -83,7 +88,7 @@ class ScipyNlpSolver:
             # exact second derivatives from the Hessian kernel (CasADi's nlp_hess_l) unless the caller asks for a
             # quasi-Newton model with IPOPT's option name
             exact = self.options.get("ipopt.hessian_approximation", self.options.get("hessian_approximation", "exact")) == "exact"
-            exact = exact and not getattr(tr, "adaptive", False)  # no Hessian kernel for the widths-as-variables NLP yet
+            exact = exact and has_hess
             if exact:
                 zero_lam = np.zeros(n_g)
 

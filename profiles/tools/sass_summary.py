@@ -6,8 +6,11 @@ import re
 import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-OBJ = os.path.join(ROOT, "mpopt_b200", "build", "mpx_aot_a8606f585eb54b8b.o")
-NAME = "_Z16mpx_gjac2_kernelI24MpxPh_a8606f585eb54b8b_0Lb1ELi15EEv12MpxPhaseArgs"
+GEN = os.path.join(ROOT, "mpopt_b200", "csrc", "gen")
+KEY = next(f[8:-3] for f in sorted(os.listdir(GEN)) if f.endswith(".cu")
+           and open(os.path.join(GEN, f)).readline().strip() == "// problem: synthetic_6_3")
+OBJ = os.path.join(ROOT, "mpopt_b200", "build", f"mpx_aot_{KEY}.o")
+NAME = f"_Z16mpx_gjac2_kernelI24MpxPh_{KEY}_0Lb1ELi15EEv12MpxPhaseArgs"
 txt = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True).stdout
 start = txt.index("Function : " + NAME)
 nxt = txt.find("Function : ", start + 20)
@@ -18,7 +21,7 @@ for l in lines:
     m = re.search(r"\*/\s+(@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", l)
     if m:
         ops[m.group(2).split(".")[0]] += 1
-print("cuobjdump -sass mpopt_b200/build/mpx_aot_a8606f585eb54b8b.o   (the object linked into the shipped libmpx.so)")
+print(f"cuobjdump -sass mpopt_b200/build/mpx_aot_{KEY}.o   (the object linked into the shipped libmpx.so)")
 print("kernel:", NAME, " = mpx_gjac2_kernel<synthetic_6_3, JAC = true, DEG = 15>")
 print("instructions:", len(lines))
 print("\nmnemonic histogram:")

@@ -113,9 +113,50 @@ def test_adaptive_plan_refuses_what_it_cannot_do(libmpx):
 
     with pytest.raises(_lib.MpxError):
         Transcription(moon_lander(), 4, 3, "LGR", adaptive=True, segments=(0, 2))
-    tr = Transcription(moon_lander(), 4, 3, "LGR", adaptive=True)
+    from mpopt_b200.problems import kitchen_sink
+
+    tr = Transcription(kitchen_sink(), 4, [3, 5, 4, 3], "LGR", adaptive=True)  # explicit time dependence
     with pytest.raises(_lib.MpxError):
         tr.hess_structure()
+
+
+HESS_CASES = [("moon_lander", 3, 3, "LGR", True), ("moon_lander", 4, [4, 2, 3, 5], "LGL", True),
+              ("hyper_sensitive", 3, [4, 2, 3], "LGR", True), ("hyper_sensitive", 5, 15, "CGL", True),
+              ("synthetic_6_3", 2, 3, "LGR", True), ("synthetic_6_3", 5, 6, "LGR", False),
+              ("van_der_pol", 3, 5, "LGR", True), ("two_phase_schwartz", 2, 4, "LGR", True),
+              ("robot_arm", 2, 4, "LGR", True)]
+
+
+@pytest.mark.parametrize("problem,K,po,scheme,mid", HESS_CASES, ids=[f"{c[0]}-{c[1]}-{c[3]}-{'res' if c[4] else 'nores'}" for c in HESS_CASES])
+def test_adaptive_hessian_matches_oracle(libmpx, problem, K, po, scheme, mid):
+    """nlp_hess_l of the widths-as-variables NLP (what ca.nlpsol derives for mpopt_adaptive, mpopt.py:757 with the NLP
+    of :3174-3205): lower triangle, pattern bit-exact, values to 1e-10 against the second-order-dual oracle (which is
+    itself checked by finite differences, tests/test_oracle_adaptive.py).  Covers the bilinear h_k = (tf - t0) w_k /
+    delta terms and the dense per-segment blocks of the mid-point residual rows."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle.adaptive import OracleAdaptiveNLP
+    from oracle.hessian import hess_l
+
+    ocp = REGISTRY[problem]()
+    tr = Transcription(ocp, K, po, scheme, adaptive=True, mid_residuals=mid)
+    ora = OracleAdaptiveNLP(ocp, K, po, scheme, mid_residuals=mid)
+    z = _point(ora, problem)
+    rng = np.random.default_rng(9)
+    lam = rng.uniform(-1, 1, tr.n_g)
+    import scipy.sparse as sp
+
+    H = hess_l(ora, z, None, 0.7, lam)
+    rp, ci = tr.hess_structure()
+    assert np.array_equal(rp, H.indptr) and np.array_equal(ci, H.indices), "Hessian pattern differs from the oracle"
+    assert_close(tr.hess_l_values(z, None, 0.7, lam), H.data, "hess_l values")
+    # constraints only (lam_f = 0; the oracle's pattern then loses the entries that only the objective has)
+    H0 = hess_l(ora, z, None, 0.0, lam)
+    G0 = sp.csr_matrix((tr.hess_l_values(z, None, 0.0, lam), ci, rp), shape=H0.shape)
+    diff = abs(G0 - H0)
+    assert diff.max() <= 1e-10 * max(1.0, abs(H0).max())
+    # evaluating twice gives the same bits (the += accumulation is ordered)
+    assert np.array_equal(tr.hess_l_values(z, None, 0.7, lam), tr.hess_l_values(z, None, 0.7, lam))
 
 
 # ---------------------------------------------------------------------------- the reference's adaptive tests
