@@ -74,14 +74,14 @@ def test_oracle_reproduces_golden_hessian(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", [n for n in HESS if len(CASES[n]) == 4])  # the adaptive NLP has no device Hessian yet
+@pytest.mark.parametrize("name", HESS)  # base NLPs and the widths-as-variables NLP (round 2: device Hessian)
 def test_cuda_reproduces_golden_hessian(libmpx, name):
     from mpopt_b200.nlp import Transcription
     from mpopt_b200.problems import REGISTRY
 
     problem, K, po, scheme = CASES[name][:4]
     G = np.load(os.path.join(sys_path_golden, name + "_hess.npz"))
-    tr = Transcription(REGISTRY[problem](), K, po, scheme, drop_exact_zeros=False)
+    tr = Transcription(REGISTRY[problem](), K, po, scheme, drop_exact_zeros=False, adaptive=len(CASES[name]) > 4)
     rp, ci = tr.hess_structure()
     assert np.array_equal(rp, G["rowptr"]) and np.array_equal(ci, G["colind"])
     assert_close(tr.hess_l_values(G["z"], G["p"], float(G["lam_f"]), G["lam_g"]), G["values"], "hess_l values")
