@@ -244,13 +244,8 @@ class Transcription:
         segment: ``xi`` (n, nx), ``ui`` (n, nu), ``ti`` (n,), and with ``derivatives`` also ``dxi``, ``dui`` and
         ``res = dxi - h Sx f``; ``counts`` is the number of points per segment."""
         z, p = self._zp(z, p)
-        if taus is None or len(taus) != self.K:
-            raise ValueError("taus must hold one array per segment")
-        counts = np.fromiter(map(len, taus), dtype=np.int64, count=self.K)
-        n = int(counts.sum())
-        seg = np.repeat(np.arange(self.K, dtype=np.int32), counts)
-        tau = np.ascontiguousarray(np.concatenate(taus), dtype=float).reshape(-1) if n else np.zeros(0)
-        counts = counts.tolist()
+        seg, tau, counts = self._pack_points(taus)
+        n = len(tau)
         out = {"xi": np.empty((n, self.nx)), "ui": np.empty((n, self.nu)), "ti": np.empty(n), "counts": counts}
         if derivatives:
             out.update(dxi=np.empty((n, self.nx)), dui=np.empty((n, self.nu)), res=np.empty((n, self.nx)))
@@ -259,6 +254,26 @@ class Transcription:
                                               _lib.ptr(seg, _lib.c_i32p), _lib.ptr(tau), ptr("xi"), ptr("ui"), ptr("ti"),
                                               ptr("dxi"), ptr("dui"), ptr("res")))
         return out
+
+    def _pack_points(self, taus):
+        """(segment of each point, local abscissa of each point, points per segment) from the reference's per-segment
+        lists; a 2-D array [K, m] (the same number of points in every segment: mid points, uniform grids) is packed
+        without a Python loop over the segments."""
+        if isinstance(taus, np.ndarray) and taus.ndim == 2:
+            if taus.shape[0] != self.K:
+                raise ValueError("taus must hold one row per segment")
+            m = taus.shape[1]
+            key = (self.K, m)
+            if getattr(self, "_seg_cache", (None,))[0] != key:
+                self._seg_cache = (key, np.repeat(np.arange(self.K, dtype=np.int32), m), [m] * self.K)
+            return self._seg_cache[1], np.ascontiguousarray(taus, dtype=float).reshape(-1), self._seg_cache[2]
+        if taus is None or len(taus) != self.K:
+            raise ValueError("taus must hold one array per segment")
+        counts = np.fromiter(map(len, taus), dtype=np.int64, count=self.K)
+        n = int(counts.sum())
+        seg = np.repeat(np.arange(self.K, dtype=np.int32), counts)
+        tau = np.ascontiguousarray(np.concatenate(taus), dtype=float).reshape(-1) if n else np.zeros(0)
+        return seg, tau, counts.tolist()
 
     def state_residuals(self, z, p=None, phase=0, taus=None):
         """State residual by quadrature at per-segment target points (mpopt.py:989-1076): ``xint`` = state at the

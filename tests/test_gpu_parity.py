@@ -622,3 +622,23 @@ def test_sharded_objective_partials_sum_to_the_full_objective(libmpx, make, K, p
     total[glob] = small
     assert abs(sum(fs) - ora.f(z, w)) <= 1e-10 * max(1.0, abs(ora.f(z, w)))
     assert_close(total, ora.grad_f(z, w), "gathered grad_f")
+
+
+@pytest.mark.gpu
+def test_residuals_accept_a_2d_array_of_points(libmpx):
+    """One [K, m] array of local abscissae (same number of points in every segment) gives what the reference's
+    per-segment lists give."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import moon_lander
+
+    K = 7
+    tr = Transcription(moon_lander(), K, 4, "LGL")
+    rng = np.random.default_rng(3)
+    z = rng.uniform(-1, 1, tr.n_z)
+    z[-2:] = [0.0, 3.0]
+    taus = rng.uniform(-1, 1, (K, 5))
+    a = tr.residuals(z, None, 0, [taus[k] for k in range(K)])
+    b = tr.residuals(z, None, 0, taus)
+    assert a["counts"] == b["counts"]
+    for key in ("xi", "ui", "ti", "dxi", "dui", "res"):
+        assert np.array_equal(a[key], b[key]), key
