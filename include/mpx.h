@@ -17,7 +17,10 @@
  *     back; *_dev entry points take device pointers and a cudaStream_t (as void*) and
  *     do no host work beyond the launch;
  *   - a plan owns its device buffers and one CUDA stream; entry points are not
- *     re-entrant on the same plan, different plans may be used concurrently.
+ *     re-entrant on the same plan (ONE evaluation per plan in flight: the launches share
+ *     the plan's argument blocks and scratch buffers, also through the *_dev entry points on
+ *     caller streams), different plans may be used concurrently.  *_dev entry points make
+ *     the plan's device current on the calling thread.
  *   - there is NO CPU fallback: without a CUDA device mpx_plan_create fails with
  *     MPX_ENODEVICE.
  */

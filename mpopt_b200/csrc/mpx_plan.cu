@@ -394,8 +394,9 @@ struct mpx_plan {
   bool hess_built = false;
   std::vector<int64_t> h_rowptr, h_colind;
   struct HessPhase {
-    DevBuf pos_yy, pos_ay, pos_ty, pos_corner, pos_term, term_assign, part, lin;
-    int blocks = 0, n_corner = 0, affine = 0;
+    DevBuf pos_yy, pos_ay, pos_ty, pos_corner, pos_term, term_assign, part;
+    MpxHessLin lin;  // affine positions of the interior nodes' entries, passed to the node kernel by value
+    int blocks = 0, n_corner = 0;
   };
   std::vector<HessPhase> hess_ph;
   DevBuf d_node_seg, d_lam, d_hvals;
@@ -615,7 +616,7 @@ struct MpxRtPhase final : MpxPhaseKernels {
                f_adaptk[2] = {nullptr, nullptr}, f_ahess[2] = {nullptr, nullptr};
   int nx_ = 0, nu_ = 0, na_ = 0;  // for the shared-memory bound of the adaptive Hessian kernel
   static cudaError_t go(CUfunction_t f, const MpxPhaseArgs& a, int grid, int threads, size_t smem, cudaStream_t st,
-                        bool pdl = false) {
+                        bool pdl = false, const void* arg2 = nullptr) {
     RtApi& R = rt_api();
     if (smem > 48 * 1024) {  // opt in to large dynamic shared memory once per function, not once per launch
       static std::vector<CUfunction_t> configured;
@@ -625,7 +626,7 @@ struct MpxRtPhase final : MpxPhaseKernels {
         configured.push_back(f);
       }
     }
-    void* params[] = {const_cast<MpxPhaseArgs*>(&a)};
+    void* params[] = {const_cast<MpxPhaseArgs*>(&a), const_cast<void*>(arg2)};
     if (pdl && R.LaunchKernelEx && mpx_pdl_enabled()) {
       RtLaunchAttr at;
       memset(&at, 0, sizeof at);
@@ -656,8 +657,8 @@ struct MpxRtPhase final : MpxPhaseKernels {
   cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const override {
     return go(f_resid[deriv], a, grid, 128, 0, st);
   }
-  cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
-    cudaError_t e = go(f_hess[0], a, grid, MPX_HESS_THREADS, 0, st);
+  cudaError_t hess(const MpxPhaseArgs& a, const MpxHessLin& hl, int grid, cudaStream_t st) const override {
+    cudaError_t e = go(f_hess[0], a, grid, MPX_HESS_THREADS, 0, st, false, &hl);
     return e != cudaSuccess || a.ticket ? e : go(f_hess[1], a, 1, MPX_HESS_FINAL_THREADS, 0, st);
   }
   cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
@@ -1858,6 +1859,16 @@ static void scan_widths(mpx_plan& p, const double* d_z, const double* d_p, cudaS
   ++p.launches;
 }
 
+// The *_dev entry points launch on the caller's stream from the caller's thread: make the plan's device current when it
+// is not (a thread whose current device differs would otherwise launch on the wrong GPU).  One evaluation per plan may
+// be in flight at a time: the launches share the plan's argument blocks and scratch buffers (include/mpx.h, Threading).
+static inline cudaError_t use_plan_device(const mpx_plan& p) {
+  int cur = -1;
+  cudaError_t e = cudaGetDevice(&cur);
+  if (e != cudaSuccess || cur == p.device) return e;
+  return cudaSetDevice(p.device);
+}
+
 static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, double* d_g, double* d_vals, cudaStream_t st) {
   const bool jac = d_vals != nullptr;
   double* target = jac ? ((p.gather.empty() || p.base_direct) ? d_vals : p.d_full.as<double>()) : nullptr;
@@ -2522,7 +2533,22 @@ int build_hessian(mpx_plan& p) {
         if (L.pat_ht[(size_t)a * NT + b]) {
           const int64_t ca = termcol(L, a), cb = termcol(L, b);
           const int64_t pos = pos_of(std::max(ca, cb), std::min(ca, cb));
-          pterm.push_back(pos), tassign.push_back(owned[pos] ? 0 : 1);
+          // who else writes this position?  (the terminal variables are x0, xf, t0, tf, a: node 0, node N-1 or the corner)
+          int own = 3;
+          if (owned[pos]) {
+            own = -1;
+            for (int c = 0; c < n_corner && own < 0; ++c)
+              if (pcorner[c] == pos) own = 2;
+            auto at_node = [&](const std::vector<int64_t>& tab, int64_t node) {
+              for (size_t q = 0; q * (size_t)N < tab.size(); ++q)
+                if (tab[q * (size_t)N + (size_t)node] == pos) return true;
+              return false;
+            };
+            if (own < 0 && (at_node(pyy, 0) || at_node(pay, 0) || at_node(pty, 0))) own = 0;
+            if (own < 0 && (at_node(pyy, N - 1) || at_node(pay, N - 1) || at_node(pty, N - 1))) own = 1;
+            if (own < 0) return fail(MPX_EINVAL, "Hessian pattern: a terminal entry shares its position with an interior node");
+          }
+          pterm.push_back(pos), tassign.push_back(own);
         }
     // rows of interior nodes are regular: position = base + i * stride (checked, not assumed)
     std::vector<int64_t> lin;
@@ -2537,9 +2563,30 @@ int build_hessian(mpx_plan& p) {
       }
     };
     add_lin(pyy, pyy.size() / (size_t)N), add_lin(pay, pay.size() / (size_t)N), add_lin(pty, 2 * nty);
-    H.affine = affine ? 1 : 0;
-    if (!affine) lin.assign(2, 0);
-    CUDA_TRY(upload(H.lin, lin.data(), lin.size() * sizeof(int64_t)));
+    memset(&H.lin, 0, sizeof H.lin);
+    if (affine && lin.size() / 2 <= MPX_HLIN_MAX) {
+      for (size_t e = 0; e < lin.size() / 2 && affine; ++e) {
+        H.lin.base[e] = lin[2 * e];
+        if (lin[2 * e + 1] < 0 || lin[2 * e + 1] > INT32_MAX) affine = false;
+        H.lin.stride[e] = (int32_t)lin[2 * e + 1];
+      }
+      H.lin.n = affine ? (int32_t)(lin.size() / 2) : 0;
+    }
+    // node-diagonal rows: are the cat-0 entries of row a adjacent, in entry order, with the rows of consecutive nodes
+    // back to back?  (true for the base NLP; the kernel then writes each row block as one contiguous run per warp)
+    H.lin.rows = H.lin.n > 0 ? 1 : 0;
+    for (int a = 0; a < ny && H.lin.rows; ++a) {
+      int len = 0, first = -1;
+      for (const HessEntry& e : ents[ph])
+        if (e.cat == 0 && e.a == a) first = first < 0 ? e.slot : first, ++len;
+      int rank = 0;
+      for (const HessEntry& e : ents[ph])
+        if (e.cat == 0 && e.a == a) {
+          if (H.lin.stride[e.slot] != len || H.lin.base[e.slot] != H.lin.base[first] + rank) H.lin.rows = 0;
+          ++rank;
+        }
+    }
+    if (const char* re = getenv("MPX_HESS_ROWS")) H.lin.rows = H.lin.rows && atoi(re) != 0;  // 0: scattered stores (measurements)
     CUDA_TRY(upload(H.pos_yy, pyy.data(), pyy.size() * sizeof(int64_t)));
     CUDA_TRY(upload(H.pos_ay, pay.data(), pay.size() * sizeof(int64_t)));
     CUDA_TRY(upload(H.pos_ty, pty.data(), pty.size() * sizeof(int64_t)));
@@ -2577,10 +2624,10 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
     a.lam = d_lam, a.lam_f = lam_f, a.node_seg = p.d_node_seg.as<int32_t>();
     a.hp_yy = H.pos_yy.as<int64_t>(), a.hp_ay = H.pos_ay.as<int64_t>(), a.hp_ty = H.pos_ty.as<int64_t>();
     a.hp_corner = H.pos_corner.as<int64_t>(), a.hp_term = H.pos_term.as<int64_t>();
-    a.hp_lin = H.lin.as<int64_t>(), a.h_affine = H.affine;
     a.hp_term_assign = H.term_assign.as<int32_t>();
     a.hvals = d_vals, a.hpart = H.part.as<double>(), a.h_blocks = H.blocks;
-    CUDA_TRY(p.prog->phases[ph]->hess(a, H.blocks, st));
+    a.trace = p.d_trace.p ? p.d_trace.as<unsigned long long>() : nullptr;  // MPX_TRACE=1: per-warp timeline stamps
+    CUDA_TRY(p.prog->phases[ph]->hess(a, H.lin, H.blocks, st));
     p.launches += a.ticket ? 1 : 2;
     if (p.adaptive) {
       a.h_rowptr = p.d_hrowptr.as<int64_t>(), a.h_colind = p.d_hcolind.as<int64_t>(), a.hpart2 = p.d_hpart2.as<double>();
@@ -2811,6 +2858,7 @@ extern "C" int mpx_fetch(mpx_plan* p, int32_t what, double* out) {
 extern "C" int mpx_eval_g_jac_dev(mpx_plan* p, const double* d_z, const double* d_p, double* d_g, double* d_values,
                                   void* stream) {
   if (!p || !d_z || (!d_p && p->n_p) || !d_g) return fail(MPX_EINVAL, "NULL argument");
+  CUDA_TRY(use_plan_device(*p));
   return launch_g_jac(*p, d_z, d_p, d_g, d_values, stream ? (cudaStream_t)stream : p->stream);
 }
 
@@ -2906,6 +2954,7 @@ extern "C" int mpx_eval_g_jac_dev_peers(mpx_plan* p, const double* d_z, const do
 extern "C" int mpx_eval_f_grad_dev(mpx_plan* p, const double* d_z, const double* d_p, double* d_f, double* d_grad,
                                    void* stream) {
   if (!p || !d_z || (!d_p && p->n_p) || !d_f) return fail(MPX_EINVAL, "NULL argument");
+  CUDA_TRY(use_plan_device(*p));
   return launch_f_grad(*p, d_z, d_p, d_f, d_grad, stream ? (cudaStream_t)stream : p->stream);
 }
 

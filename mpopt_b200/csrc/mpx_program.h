@@ -22,7 +22,7 @@ struct MpxPhaseKernels {
   virtual cudaError_t fgrad(const MpxPhaseArgs& a, bool grad, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t fgrad_final(const MpxPhaseArgs& a, bool grad, cudaStream_t st) const = 0;
   virtual cudaError_t residual(const MpxPhaseArgs& a, bool deriv, int grid, cudaStream_t st) const = 0;
-  virtual cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const = 0;  // node kernel + final
+  virtual cudaError_t hess(const MpxPhaseArgs& a, const MpxHessLin& hl, int grid, cudaStream_t st) const = 0;  // node kernel + final
   // widths-as-variables NLP (mpopt_adaptive): extra rows / columns, and d f / d w
   virtual cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const = 0;
   virtual cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const = 0;
@@ -204,8 +204,8 @@ struct MpxAotPhase final : MpxPhaseKernels {
     else mpx_residual_kernel<PH, false><<<grid, 128, 0, st>>>(a);
     return cudaGetLastError();
   }
-  cudaError_t hess(const MpxPhaseArgs& a, int grid, cudaStream_t st) const override {
-    mpx_hess_kernel<PH><<<grid, MPX_HESS_THREADS, 0, st>>>(a);
+  cudaError_t hess(const MpxPhaseArgs& a, const MpxHessLin& hl, int grid, cudaStream_t st) const override {
+    mpx_hess_kernel<PH><<<grid, MPX_HESS_THREADS, 0, st>>>(a, hl);
     if (!a.ticket) mpx_hess_final<PH><<<1, MPX_HESS_FINAL_THREADS, 0, st>>>(a);  // else done by the node kernel's last CTA
     return cudaGetLastError();
   }

@@ -421,6 +421,8 @@ class Program:
         self.nx, self.nu, self.na, self.n_phases = ocp.nx, ocp.nu, ocp.na, ocp.n_phases
         self.phases = [PhaseProgram(ocp, ph) for ph in range(ocp.n_phases)]
         self._src = None
+        self.cuda_source()
+        tr.Expr.reset_interning()  # the traced DAG is finished: do not let the intern table grow with every OCP
 
     def cuda_source(self) -> str:
         """Canonical generated source: one struct per phase, named by position only (so the hash is stable)."""

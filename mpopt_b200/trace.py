@@ -25,11 +25,18 @@ _UNARY = ("neg", "sqrt", "exp", "log", "sin", "cos", "tan", "asin", "acos", "ata
 _BINARY = ("add", "sub", "mul", "div", "pow")
 
 _FOLD1 = {
-    "neg": lambda a: -a, "sqrt": math.sqrt, "exp": math.exp, "log": math.log, "sin": math.sin,
-    "cos": math.cos, "tan": math.tan, "asin": math.asin, "acos": math.acos, "atan": math.atan,
-    "sinh": math.sinh, "cosh": math.cosh, "tanh": math.tanh, "fabs": abs,
-    "sign": lambda a: (a > 0) - (a < 0), "sq": lambda a: a * a,
+    "neg": np.negative, "sqrt": np.sqrt, "exp": np.exp, "log": np.log, "sin": np.sin,
+    "cos": np.cos, "tan": np.tan, "asin": np.arcsin, "acos": np.arccos, "atan": np.arctan,
+    "sinh": np.sinh, "cosh": np.cosh, "tanh": np.tanh, "fabs": np.abs,
+    "sign": np.sign, "sq": np.square,
 }
+
+
+def _fold(fn, *vals):
+    """Constant folding in IEEE arithmetic: out-of-domain arguments, overflow and division by zero give nan / inf
+    like CasADi's SX folds do (the Python math module would raise instead and abort the trace)."""
+    with np.errstate(all="ignore"):
+        return float(fn(*(np.float64(v) for v in vals)))
 
 
 class Expr:
@@ -51,6 +58,15 @@ class Expr:
         Expr._count += 1
         cls._intern[key] = self
         return self
+
+    @classmethod
+    def reset_interning(cls):
+        """Forget every interned node except the shared constants (call between traced problems in a long-lived
+        process: the table otherwise grows with every OCP).  Expressions created before the reset stay valid but no
+        longer unify with new ones, so never mix the two in one program."""
+        keep = {k: v for k, v in cls._intern.items() if v.op == "const" and v.value in (0.0, 1.0)}
+        cls._intern.clear()
+        cls._intern.update(keep)
 
     # ---- predicates
     @property
@@ -151,7 +167,7 @@ def as_expr(v) -> Expr:
 def unary(op: str, a) -> Expr:
     a = as_expr(a)
     if a.is_const:
-        return const(_FOLD1[op](a.value))
+        return const(_fold(_FOLD1[op], a.value))
     if op == "neg" and a.op == "neg":
         return a.args[0]
     return Expr(op, (a,))
@@ -188,7 +204,7 @@ def sub(a, b) -> Expr:
 def mul(a, b) -> Expr:
     a, b = as_expr(a), as_expr(b)
     if a.is_const and b.is_const:
-        return const(a.value * b.value)
+        return const(_fold(np.multiply, a.value, b.value))
     if a.is_value(0.0) or b.is_value(0.0):
         return ZERO
     if a.is_value(1.0):
@@ -207,7 +223,7 @@ def mul(a, b) -> Expr:
 def div(a, b) -> Expr:
     a, b = as_expr(a), as_expr(b)
     if a.is_const and b.is_const:
-        return const(a.value / b.value)
+        return const(_fold(np.divide, a.value, b.value))
     if a.is_value(0.0):
         return ZERO
     if b.is_value(1.0):
@@ -220,7 +236,7 @@ def div(a, b) -> Expr:
 def power(a, b) -> Expr:
     a, b = as_expr(a), as_expr(b)
     if a.is_const and b.is_const:
-        return const(a.value ** b.value)
+        return const(_fold(np.power, a.value, b.value))
     if b.is_const:
         e = b.value
         if e == 0.0:

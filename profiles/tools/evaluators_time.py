@@ -10,6 +10,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from mpopt_b200 import _lib  # noqa: E402
 from mpopt_b200.nlp import Transcription  # noqa: E402
 from mpopt_b200.problems import synthetic_6_3  # noqa: E402
@@ -38,18 +39,13 @@ calls = {
     "f + grad_f (mpx_eval_f_grad_dev)": (lambda: tr.f_grad_dev(zd.data_ptr(), pd.data_ptr(), f.data_ptr(), grad.data_ptr(), sp), 8 * (2 * tr.n_z + tr.n_p)),
     "hess_l (mpx_eval_hess_l_dev)": (lambda: _lib.check(L.mpx_eval_hess_l_dev(tr._plan, zd.data_ptr(), pd.data_ptr(), C.c_double(0.7), lam.data_ptr(), hv.data_ptr(), sp)), 8 * (tr.n_z + tr.n_p + tr.n_g + nh)),  # z, p, multipliers read, every entry written once
 }
+from _timing import time_call  # noqa: E402
+
 for name, (fn, nbytes) in calls.items():
-    for _ in range(5):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(100):
-        fn()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    us = e0.elapsed_time(e1) * 10
-    print(json.dumps({"evaluator": name, "us": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2), "GBs": round(nbytes / us / 1e3, 1)}))
+    host_us, graph_us = time_call(fn, stream, n=50)
+    us = graph_us if graph_us is not None else host_us
+    print(json.dumps({"evaluator": name, "us": round(us, 2), "host_issued_us": round(host_us, 2), "algorithmic_MB": round(nbytes / 1e6, 2),
+                      "GBs": round(nbytes / us / 1e3, 1), "timing": "CUDA-graph replay of 50 calls" if graph_us is not None else "host-issued"}))
 print(json.dumps({"nnz_jac": tr.nnz, "nnz_hess_lower": nh}))
 
 # the inner step of every h-adaptive pass: dynamics residual at the mid points of all segments (host-pointer entry

@@ -91,3 +91,31 @@ def test_row_layouts_moon_lander():
     assert pp.f_row_layout(0) == ([], [("x", 1), ("T0", 0), ("TF", 0)])
     assert pp.f_row_layout(1) == ([], [("u", 0), ("T0", 0), ("TF", 0)])
     assert pp.tc_row_layout(0) == [0] and pp.tc_row_layout(1) == [1]
+
+
+def test_constant_folding_follows_ieee_like_sx():
+    """Out-of-domain constants fold to nan / inf instead of aborting the trace (CasADi's SX folds the same way)."""
+    import math
+
+    from mpopt_b200 import trace as tr
+
+    assert math.isnan(tr.unary("sqrt", -1.0).value) and math.isnan(tr.unary("acos", 2.0).value)
+    assert tr.unary("log", 0.0).value == -math.inf and tr.unary("exp", 1000.0).value == math.inf
+    assert tr.div(1.0, 0.0).value == math.inf and tr.div(-1.0, 0.0).value == -math.inf
+    assert tr.power(0.0, -1.0).value == math.inf and math.isnan(tr.div(0.0, 0.0).value)
+    lines, refs = tr.emit_c([tr.mul(tr.var("x"), tr.unary("sqrt", -1.0))], {"x": "x[0]"})
+    assert "(0.0/0.0)" in "".join(lines)
+
+
+def test_interning_is_scoped_to_a_program():
+    """The intern table does not grow with every traced OCP, and the generated source does not depend on what was
+    traced before (the hash selects the AOT object)."""
+    from mpopt_b200 import problems, trace as tr
+    from mpopt_b200.program import Program
+
+    k1 = Program(problems.moon_lander()).key()
+    n1 = len(tr.Expr._intern)
+    Program(problems.van_der_pol())
+    Program(problems.hyper_sensitive())
+    assert len(tr.Expr._intern) == n1 <= 4
+    assert Program(problems.moon_lander()).key() == k1
