@@ -365,6 +365,7 @@ struct mpx_plan {
   DevBuf d_rseg, d_rtau, d_rout;                   // mpx_eval_residuals: point list and outputs
   DevBuf d_sr_off, d_sr_out;                       // mpx_eval_state_residuals: point offsets per segment, outputs
   int smem_adapt = 0;
+  int adapt_grid = 1 << 30;  // CTAs of the persistent mpx_adapt_kernel (MPX_ADAPT_CTAS per SM; segments when there is no queue)
   std::vector<int> adapt_img;              // per phase: doubles of a staged residual-row image (0: direct stores)
   std::vector<int64_t> sw_direct;          // per phase: CSR position of the SW block when it is written in place, else -1
   std::vector<int64_t> gather_runs;        // (first, count) CSR ranges that go through the gather (empty: everything)
@@ -1457,7 +1458,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
       njf = std::max(njf, n);
     }
     const int n1 = dmax + 1;  // same formula as mpx_adapt_smem_doubles
-    p.smem_adapt = 8 * (MpxTab::pad2(n1) + 2 * MpxTab::pad2(dmax * n1) + MpxTab::pad2((nx + nu) * n1) +
+    p.smem_adapt = 8 * (MpxTab::pad2(n1) + 2 * MpxTab::pad2(dmax * n1) + 2 * MpxTab::pad2((nx + nu) * n1) + 2 +
                         MpxTab::pad2(dmax * (3 * nx + njf + 2)) + MpxTab::pad2(dmax * (2 * nx + nu)) + MPX_THREADS);
     if (p.smem_adapt > 227 * 1024) return fail(MPX_ELIMIT, "polynomial degree too large for the adaptive NLP kernel");
     // residual-row images for the bulk-copy engine: two per CTA, when no row carries the K-wide width block of
@@ -1499,8 +1500,8 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   {
     const char* qe = getenv("MPX_QUEUE");  // 0: units dealt round-robin (measurements)
     if (!qe || atoi(qe)) {
-      CUDA_TRY(p.d_queue.ensure((size_t)2 * p.P * sizeof(unsigned int)));
-      CUDA_TRY(cudaMemset(p.d_queue.p, 0, (size_t)2 * p.P * sizeof(unsigned int)));
+      CUDA_TRY(p.d_queue.ensure((size_t)4 * p.P * sizeof(unsigned int)));
+      CUDA_TRY(cudaMemset(p.d_queue.p, 0, (size_t)4 * p.P * sizeof(unsigned int)));
     }
   }
   {
@@ -1893,7 +1894,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
       MpxPhaseArgs& a = p.args[ph];
       a.z = d_z, a.w = widths_of(p, d_z, d_p, ph), a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
       a.g = d_g, a.vals = target, a.v4_nbuf = p.v2_nbuf;
-      a.queue = p.d_queue.p ? p.d_queue.as<unsigned int>() + 2 * ph : nullptr;
+      a.queue = p.d_queue.p ? p.d_queue.as<unsigned int>() + 4 * ph : nullptr;
       if (p.d_trace.p) a.trace = nullptr;
     }
     MpxEvArgs ev{};
@@ -1920,7 +1921,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
         CUDA_TRY(p.prog->phases[ph]->gjac4(a, jac, p.spec_deg, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
     } else if (p.v2_warps > 0) {
       a.v4_nbuf = p.v2_nbuf;
-      a.queue = p.d_queue.p ? p.d_queue.as<unsigned int>() + 2 * ph : nullptr;
+      a.queue = p.d_queue.p ? p.d_queue.as<unsigned int>() + 4 * ph : nullptr;
       if (p.d_trace.p)
         a.trace = p.d_trace.as<unsigned long long>() + (size_t)(p.trace_seq++ % MPX_TRACE_RING) * p.v2_grid * p.v2_warps * MPX_TRACE_SLOTS;
       const size_t sm2 = jac ? p.v2_smem_jac : p.v2_smem_g;
@@ -1936,7 +1937,16 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
     if (p.adaptive) {  // SW rows and the d/dw entries, staged behind the base kernels' values
       a.ad_jac = jac ? 1 : 0, a.ext = jac ? p.d_full.as<double>() + p.n_base : nullptr;
       a.ext_sw = !jac ? nullptr : (p.sw_direct[ph] >= 0 ? d_vals + p.sw_direct[ph] - L.eSum : a.ext);
-      CUDA_TRY(p.prog->phases[ph]->adapt(a, p.K, (size_t)p.smem_adapt + (jac ? 2 * (size_t)(a.ad_img + 2) * 8 : 0), st));
+      if (p.d_trace.p) a.trace = (size_t)p.K * MPX_TRACE_SLOTS <= (size_t)MPX_TRACE_RING * p.v2_grid * p.v2_warps * MPX_TRACE_SLOTS
+                                     ? p.d_trace.as<unsigned long long>() : nullptr;  // MPX_TRACE=1: per-CTA timeline
+      a.queue = p.d_queue.p ? p.d_queue.as<unsigned int>() + 4 * ph : nullptr;
+      if (p.adapt_grid == (1 << 30) && a.queue) {  // persistent CTAs: a few per SM, segments dealt out through the counter
+        int nsm = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, p.device));
+        const char* ce = getenv("MPX_ADAPT_CTAS");
+        p.adapt_grid = std::max(1, nsm * (ce && atoi(ce) > 0 ? atoi(ce) : 4));
+      }
+      CUDA_TRY(p.prog->phases[ph]->adapt(a, std::min(p.K, p.adapt_grid), (size_t)p.smem_adapt + (jac ? 2 * (size_t)(a.ad_img + 2) * 8 : 0), st));
       ++p.launches;
     }
     if (L.has_dU) {
