@@ -398,11 +398,12 @@ struct mpx_plan {
   struct HessPhase {
     DevBuf pos_yy, pos_ay, pos_ty, pos_corner, pos_term, term_assign, part;
     MpxHessLin lin;  // affine positions of the interior nodes' entries, passed to the node kernel by value
+    DevBuf ah_pos, ah_off;  // adaptive NLP: positions of what a segment adds (mpx_adapt_hess_kernel), [K + 1] offsets
     int blocks = 0, n_corner = 0;
   };
   std::vector<HessPhase> hess_ph;
   DevBuf d_node_seg, d_lam, d_hvals;
-  DevBuf d_hrowptr, d_hcolind, d_hpart2;  // adaptive NLP: Hessian pattern on the device, per-segment corner partials
+  DevBuf d_hpart2;  // adaptive NLP: per-segment corner partials
   std::vector<int64_t> h_tail_runs[2];  // rows of the small tail kernels (mpx_eval_g_jac_dev_peers)
   std::vector<int64_t> h_runs[3];  // shard plans: (offset, count) runs of g / values / grad_f written by this shard
   int staged = 0;                  // MPX_STAGE_* results currently valid in the device buffers (mpx_stage / mpx_fetch)
@@ -674,7 +675,8 @@ struct MpxRtPhase final : MpxPhaseKernels {
     // the functor's NRG / NRH are not known on the host: bound them by the number of node variables
     const int n1 = dmax + 1, ny = nx_ + nu_, nv = ny + na_, nr = 1 + nv + nv * (nv + 1) / 2;
     const size_t dbl = 2 * (size_t)MpxTab::pad2(dmax * n1) + MpxTab::pad2(n1) + MpxTab::pad2(ny * n1) + MpxTab::pad2(ny * dmax) +
-                       MpxTab::pad2(dmax * nr) + MpxTab::pad2(n1 * (1 + nv)) + MpxTab::pad2(nx_ * dmax) + 4;
+                       MpxTab::pad2(dmax * nr) + MpxTab::pad2(n1 * (1 + nv)) + MpxTab::pad2(nx_ * dmax) + 4 +
+                       (size_t)(1 + MPX_THREADS / 32) * n1 * mpx_ahess_stride(dmax) + (size_t)(3 * ny + nv * (nv + 1) / 2) * n1 + na_ + 3;
     return go(f_ahess[0], a, grid, MPX_THREADS, dbl * sizeof(double), st);
   }
   cudaError_t adapt_hess_final(const MpxPhaseArgs& a, cudaStream_t st) const override { return go(f_ahess[1], a, 1, 64, 0, st); }
@@ -2617,10 +2619,45 @@ int build_hessian(mpx_plan& p) {
     CUDA_TRY(H.part.ensure((size_t)H.blocks * n_corner * sizeof(double)));
   }
   if (p.adaptive) {
-    CUDA_TRY(p.d_hrowptr.ensure(p.h_rowptr.size() * sizeof(int64_t)));
-    CUDA_TRY(p.d_hcolind.ensure(std::max<size_t>(p.h_colind.size(), 1) * sizeof(int64_t)));
-    CUDA_TRY(cudaMemcpy(p.d_hrowptr.p, p.h_rowptr.data(), p.h_rowptr.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMemcpy(p.d_hcolind.p, p.h_colind.data(), p.h_colind.size() * sizeof(int64_t), cudaMemcpyHostToDevice));
+    // Positions of everything a segment adds, looked up ONCE here (the kernel used to find each entry by binary search
+    // in a 178 MB column-index array).  Per segment, with n1 = degree + 1 and e over the second derivatives of psi:
+    //   [ny][n1] (w_k, Y_jb) | [ny][n1] (T0, Y_jb) | [ny][n1] (TF, Y_jb) | [NRH][n1]: first entry of the run
+    //   (Y_j va, Y_0 vb) of a dense block, or the single entry (a_m, Y_j vb) | [na] (w_k, a_m) | (w_k, T0), (w_k, TF), (w_k, w_k)
+    // -1: not in the pattern (the value is an exact zero).
+    auto find_pos = [&](int64_t r, int64_t c) -> int64_t {
+      const int64_t* b = p.h_colind.data() + p.h_rowptr[(size_t)r];
+      const int64_t* e = p.h_colind.data() + p.h_rowptr[(size_t)r + 1];
+      const int64_t* q = std::lower_bound(b, e, c);
+      return (q < e && *q == c) ? (int64_t)(q - p.h_colind.data()) : -1;
+    };
+    for (int ph = 0; ph < p.P; ++ph) {
+      const PhaseLayout& L = p.ph[ph];
+      std::vector<std::pair<int, int>> rh;
+      for (int a = 0; a < nv; ++a)
+        for (int b = 0; b <= a; ++b)
+          if (L.pat_hf[(size_t)a * nv + b]) rh.emplace_back(a, b);
+      std::vector<int64_t> off((size_t)p.K + 1, 0), pos;
+      for (int k = 0; k < p.K; ++k) {
+        const int s0 = p.seg_start[k], n1 = p.po[k] + 1;
+        const int64_t cW = colT0(L) + 2 + na + k;
+        off[(size_t)k] = (int64_t)pos.size();
+        for (int sec = 0; sec < 3; ++sec)
+          for (int b = 0; b < ny; ++b)
+            for (int j = 0; j < n1; ++j)
+              pos.push_back(find_pos(sec == 0 ? cW : colT0(L) + (sec - 1), colv(L, b, s0 + j)));
+        for (auto& ab : rh)
+          for (int j = 0; j < n1; ++j) {
+            if (ab.first < ny) pos.push_back(find_pos(colv(L, ab.first, s0 + j), colv(L, ab.second, s0)));
+            else if (ab.second < ny) pos.push_back(find_pos(colA(L, ab.first - ny), colv(L, ab.second, s0 + j)));
+            else pos.push_back(-1);
+          }
+        for (int m = 0; m < na; ++m) pos.push_back(find_pos(cW, colA(L, m)));
+        pos.push_back(find_pos(cW, colT0(L))), pos.push_back(find_pos(cW, colT0(L) + 1)), pos.push_back(find_pos(cW, cW));
+      }
+      off[(size_t)p.K] = (int64_t)pos.size();
+      CUDA_TRY(upload(p.hess_ph[ph].ah_pos, pos.data(), pos.size() * sizeof(int64_t)));
+      CUDA_TRY(upload(p.hess_ph[ph].ah_off, off.data(), off.size() * sizeof(int64_t)));
+    }
     CUDA_TRY(p.d_hpart2.ensure((size_t)p.K * (3 + 2 * na + na * (na + 1) / 2) * sizeof(double)));
   }
   CUDA_TRY(p.d_lam.ensure((size_t)p.n_g * sizeof(double)));
@@ -2650,7 +2687,8 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
     CUDA_TRY(p.prog->phases[ph]->hess(a, H.lin, H.blocks, st));
     p.launches += a.ticket ? 1 : 2;
     if (p.adaptive) {
-      a.h_rowptr = p.d_hrowptr.as<int64_t>(), a.h_colind = p.d_hcolind.as<int64_t>(), a.hpart2 = p.d_hpart2.as<double>();
+      a.hpart2 = p.d_hpart2.as<double>();
+      a.ah_pos = H.ah_pos.as<int64_t>(), a.ah_off = H.ah_off.as<int64_t>();
       const int dmax = *std::max_element(p.po.begin(), p.po.end());
       for (int par = 0; par < 2; ++par) {
         const int grid = (p.K - par + 1) / 2;
