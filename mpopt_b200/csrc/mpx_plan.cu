@@ -364,6 +364,7 @@ struct mpx_plan {
   DevBuf d_queue;                                  // [P][2] dynamic unit queue of the g + jac kernel (MPX_QUEUE=0: static)
   DevBuf d_rseg, d_rtau, d_rout;                   // mpx_eval_residuals: point list and outputs
   DevBuf d_sr_off, d_sr_out;                       // mpx_eval_state_residuals: point offsets per segment, outputs
+  bool v2_spread = true;
   int smem_adapt = 0;
   int adapt_grid = 1 << 30;  // CTAs of the persistent mpx_adapt_kernel (MPX_ADAPT_CTAS per SM; segments when there is no queue)
   std::vector<int> adapt_img;              // per phase: doubles of a staged residual-row image (0: direct stores)
@@ -1637,7 +1638,15 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
       }
       p.v2_units = (int)uk.size();
       p.v2_warps = std::max(1, std::min(warps, (p.v2_units + prop.multiProcessorCount - 1) / prop.multiProcessorCount));
-      p.v2_grid = std::min(prop.multiProcessorCount, (p.v2_units + p.v2_warps - 1) / p.v2_warps);
+      {
+        // consecutive units on different SMs (MPX_F_SPREAD) when the units differ in cost (mixed degrees, sorted longest
+        // first: config 3 8.65 -> 7.68 us) or do not fill the machine (config 5 6.76 -> 6.04 us); a full uniform plan keeps
+        // CTA b on units [b * warps, (b + 1) * warps) (headline 18.13 vs 18.3 us).  MPX_V2_SPREAD=0/1 forces either.
+        const char* sp = getenv("MPX_V2_SPREAD");
+        p.v2_spread = sp ? atoi(sp) != 0 : (!p.uniform || 2L * p.v2_units <= (long)prop.multiProcessorCount * warps);
+      }
+      p.v2_grid = p.v2_spread ? std::min(prop.multiProcessorCount, p.v2_units)
+                              : std::min(prop.multiProcessorCount, (p.v2_units + p.v2_warps - 1) / p.v2_warps);
       p.v2_stage_cap = stage_cap;
       // a second image per warp (the engine drains one while the next is assembled) when it fits
       p.v2_nbuf = (long)p.v2_warps * (per_warp + (long)(stage_cap + 2) * 8) <= avail ? 2 : 1;
@@ -1678,6 +1687,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
     // round trip before the first image is ready (MPX_CONST_FIRST=0 restores the old order, for measurements)
     const char* cf = getenv("MPX_CONST_FIRST");
     if (!cf || atoi(cf)) a.flags |= MPX_F_CONST_FIRST;
+    if (p.v2_spread) a.flags |= MPX_F_SPREAD;
     a.accumulate_f = ph > 0;
     a.zoff = L.zoff;
     a.gF = L.gF, a.gC = L.gC, a.gDU = L.gDU, a.gmU = L.gmU, a.gTC = L.gTC;

@@ -15,7 +15,7 @@ txt = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True
 start = txt.index("Function : " + NAME)
 nxt = txt.find("Function : ", start + 20)
 body = txt[start: nxt if nxt > 0 else len(txt)]
-lines = [l for l in body.splitlines() if re.search(r"/\*[0-9a-f]{4}\*/", l)]
+lines = [l for l in body.splitlines() if re.search(r"/\*[0-9a-f]{4,6}\*/", l)]
 ops = collections.Counter()
 for l in lines:
     m = re.search(r"\*/\s+(@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", l)
