@@ -524,6 +524,27 @@ def run_cuda(args):
            "ms_per_step": dt * 1e3, "steps": n_e2e,
            "api": "mpx_eval_jac_g (host pointers, pinned buffers)" + ("" if world == 1 else
                   "; per rank: its own shard over its own PCIe link, bytes are per rank")}
+    # calibration of the host link: NOTHING but the same number of bytes copied device -> pinned host memory by every rank
+    # at the same time (torch copies, no kernel of this repo): what the box can move.  When e2e's ms_per_step is close to
+    # this figure the limiter is the host side of the box (all GPUs of these boxes hang off one NUMA node), not the path.
+    try:
+        src = torch.empty(int(d2h) // 8, dtype=torch.float64, device=dev)
+        dsth = torch.empty(int(d2h) // 8, dtype=torch.float64).pin_memory()
+        for _ in range(2):
+            dsth.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            dsth.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+        dtc = max_over_ranks(time.perf_counter() - t0) / n_e2e
+        e2e["d2h_copy_only_ms_per_step"] = dtc * 1e3
+        e2e["d2h_copy_only_gbs_all_ranks"] = world * d2h / dtc / 1e9
+        del src, dsth
+    except Exception as ex:  # the calibration must never take the bench line down
+        e2e["d2h_copy_only_ms_per_step"] = None
+        print("# host-link calibration skipped:", str(ex)[:100], file=sys.stderr)
     # ---- the same end to end, other ways a caller can hand over its buffers (N = 1; reported beside `e2e`, never as
     #      the roofline): plain pageable numpy arrays (what IPOPT / CasADi allocate), the caller's pageable arrays
     #      registered once with mpx_host_register, the dynamic fetch into a registered array (only the z-dependent

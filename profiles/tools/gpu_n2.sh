@@ -12,7 +12,7 @@ for f in ("bench","bench_c4"):
         d=json.load(open("gpurun_out/n$N/%s.json"%f))
     except Exception as e:
         print(f, "no json", e); continue
-    print(f, "value", round(d["value"],1), d["scaling"], "ms", round(d["ms_per_step"]*1e3,2), "frac", round(d["roofline"]["frac"],3), "e2e", round(d["e2e"]["value"],1))
+    print(f, "value", round(d["value"],1), d["scaling"], "ms", round(d["ms_per_step"]*1e3,2), "frac", round(d["roofline"]["frac"],3), "e2e", round(d["e2e"]["value"],1), "e2e ms", round(d["e2e"]["ms_per_step"],2), "copy-only ms", d["e2e"].get("d2h_copy_only_ms_per_step"))
     for k in ("allgather","allgather_nccl"):
         a=d.get(k)
         if a: print("  ",k, {x:(round(v,3) if isinstance(v,float) else v) for x,v in a.items() if x not in ("how","note")})
