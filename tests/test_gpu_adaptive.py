@@ -124,7 +124,10 @@ HESS_CASES = [("moon_lander", 3, 3, "LGR", True), ("moon_lander", 4, [4, 2, 3, 5
               ("hyper_sensitive", 3, [4, 2, 3], "LGR", True), ("hyper_sensitive", 5, 15, "CGL", True),
               ("synthetic_6_3", 2, 3, "LGR", True), ("synthetic_6_3", 5, 6, "LGR", False),
               ("van_der_pol", 3, 5, "LGR", True), ("two_phase_schwartz", 2, 4, "LGR", True),
-              ("robot_arm", 2, 4, "LGR", True)]
+              ("robot_arm", 2, 4, "LGR", True),
+              # degrees above 15: the dense blocks leave the tensor-core path for the per-warp product tiles
+              ("hyper_sensitive", 2, 20, "LGR", True), ("van_der_pol", 3, [18, 4, 17], "LGL", True),
+              ("synthetic_6_3", 2, [16, 15], "CGL", True)]
 
 
 @pytest.mark.parametrize("problem,K,po,scheme,mid", HESS_CASES, ids=[f"{c[0]}-{c[1]}-{c[3]}-{'res' if c[4] else 'nores'}" for c in HESS_CASES])
