@@ -361,7 +361,8 @@ struct mpx_plan {
   std::vector<double> h_dmid;              // D at the mid points, [d][d+1] per degree
   DevBuf d_dmid, d_seg_dmid, d_wpart, d_seg_rpre;  // d_seg_rpre: [P][K]
   DevBuf d_ticket;                                 // [P] arrival counters of the single-launch f + grad_f kernel
-  DevBuf d_queue;                                  // [P][2] dynamic unit queue of the g + jac kernel (MPX_QUEUE=0: static)
+  DevBuf d_queue;                                  // [P][4] work counters: K2's dynamic unit queue, mpx_adapt_kernel's segment queue (MPX_QUEUE=0: none)
+  bool k2_queue = false;                           // K2 deals its units through the counter (MPX_K2_QUEUE=1; measured neutral, off by default)
   DevBuf d_rseg, d_rtau, d_rout;                   // mpx_eval_residuals: point list and outputs
   DevBuf d_sr_off, d_sr_out;                       // mpx_eval_state_residuals: point offsets per segment, outputs
   bool v2_spread = true;
@@ -1503,6 +1504,7 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
   {
     const char* qe = getenv("MPX_QUEUE");  // 0: units dealt round-robin (measurements)
     if (!qe || atoi(qe)) {
+      if (const char* k2 = getenv("MPX_K2_QUEUE")) p.k2_queue = atoi(k2) != 0;
       CUDA_TRY(p.d_queue.ensure((size_t)4 * p.P * sizeof(unsigned int)));
       CUDA_TRY(cudaMemset(p.d_queue.p, 0, (size_t)4 * p.P * sizeof(unsigned int)));
     }
@@ -1906,7 +1908,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
       MpxPhaseArgs& a = p.args[ph];
       a.z = d_z, a.w = widths_of(p, d_z, d_p, ph), a.sig0 = p.d_sig0.as<double>() + (int64_t)ph * p.K;
       a.g = d_g, a.vals = target, a.v4_nbuf = p.v2_nbuf;
-      a.queue = p.d_queue.p ? p.d_queue.as<unsigned int>() + 4 * ph : nullptr;
+      a.queue = (p.d_queue.p && p.k2_queue) ? p.d_queue.as<unsigned int>() + 4 * ph : nullptr;
       if (p.d_trace.p) a.trace = nullptr;
     }
     MpxEvArgs ev{};
@@ -1933,7 +1935,7 @@ static int launch_g_jac(mpx_plan& p, const double* d_z, const double* d_p, doubl
         CUDA_TRY(p.prog->phases[ph]->gjac4(a, jac, p.spec_deg, p.v4_grid[ph], p.v4_threads[ph], sm4, st));
     } else if (p.v2_warps > 0) {
       a.v4_nbuf = p.v2_nbuf;
-      a.queue = p.d_queue.p ? p.d_queue.as<unsigned int>() + 4 * ph : nullptr;
+      a.queue = (p.d_queue.p && p.k2_queue) ? p.d_queue.as<unsigned int>() + 4 * ph : nullptr;
       if (p.d_trace.p)
         a.trace = p.d_trace.as<unsigned long long>() + (size_t)(p.trace_seq++ % MPX_TRACE_RING) * p.v2_grid * p.v2_warps * MPX_TRACE_SLOTS;
       const size_t sm2 = jac ? p.v2_smem_jac : p.v2_smem_g;
