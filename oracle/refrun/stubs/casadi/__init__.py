@@ -679,7 +679,7 @@ def _M(x):
             for i, m in enumerate(items):
                 a[i, 0] = m.a.flat[0]
             return _wrap(a, *items)
-        return horzcat(*[m.T for m in items]).T  # list of rows
+        return vertcat(*[m.T for m in items])  # list of rows
     raise TypeError(f"cannot convert {type(x).__name__} to SX")
 
 
@@ -1028,11 +1028,72 @@ def integrator(name, plugin, dae, opts=None, *rest):
 
 
 class _NlpSolver:
+    """``ca.nlpsol(name, "ipopt", {x, f, g, p}, opts)``: IPOPT is not installable either, so a call hands the NLP's
+    evaluators (values and sparse first / second derivatives of the recorded graph) to the interior-point method of
+    ``mpopt_b200.ipm`` -- the five callbacks IPOPT would get -- and returns CasADi's result dictionary."""
+
     def __init__(self, name, plugin, nlp, opts):
         self.name, self.plugin, self.nlp, self.opts = name, plugin, nlp, dict(opts or {})
+        x = _M(nlp["x"])
+        self.has_p = "p" in nlp and _M(nlp["p"]).a.size > 0
+        g = _M(nlp["g"]) if "g" in nlp else DM._mk(_obj((0, 1)))
+        ins = [x, _M(nlp["p"])] if self.has_p else [x]
+        self.fn = Function(name, ins, [g, _M(nlp["f"])])
+        self.n, self.m = x.a.size, g.a.size
+        self.stats_ = {}
 
-    def __call__(self, **kw):
-        raise NotImplementedError("the CasADi stand-in records the NLP; it does not solve it")
+    def stats(self):
+        return self.stats_
+
+    def __call__(self, x0=None, p=None, lbx=-inf, ubx=inf, lbg=-inf, ubg=inf, lam_x0=None, lam_g0=None, **_):
+        import scipy.sparse as sp
+
+        from mpopt_b200.ipm import solve_nlp
+
+        n, m = self.n, self.m
+        vec = lambda v, k: np.broadcast_to(np.asarray(_M(v).full() if isinstance(v, SX) else v, float).ravel(), (k,)).copy() \
+            if np.size(v) in (1, k) else np.asarray(v, float).ravel()
+        pv = vec(p, _M(self.nlp["p"]).a.size) if self.has_p else None
+        cache = {}
+
+        def at(xx):
+            key = xx.tobytes()
+            if cache.get("key") != key:
+                (g, dg, hg), (f, df, hf) = self.fn.forward2_sparse([xx, pv] if self.has_p else [xx], wrt=0)
+                cache.update(key=key, g=g, dg=dg, hg=hg, f=float(f[0]), df=df[0], hf=hf[0])
+            return cache
+
+        def grad_f(xx):
+            out = np.zeros(n)
+            for c_, v in at(xx)["df"].items():
+                out[c_] = v
+            return out
+
+        def jac_g(xx):
+            rows, cols, vals = [], [], []
+            for i, row in enumerate(at(xx)["dg"]):
+                for c_, v in row.items():
+                    rows.append(i), cols.append(c_), vals.append(v)
+            return sp.csr_matrix((vals, (rows, cols)), shape=(m, n))
+
+        def hess_l(xx, lam_f, lam_g):
+            c = at(xx)
+            H = {k_: lam_f * v for k_, v in c["hf"].items()}
+            for l, h in zip(lam_g, c["hg"]):
+                for k_, v in h.items():
+                    H[k_] = H.get(k_, 0.0) + l * v
+            ks = list(H)
+            return sp.csr_matrix(([H[k_] for k_ in ks], ([k_[0] for k_ in ks], [k_[1] for k_ in ks])), shape=(n, n))
+
+        tol = float(self.opts.get("ipopt.tol", 1e-8))
+        r = solve_nlp(lambda xx: at(xx)["f"], grad_f, lambda xx: at(xx)["g"].copy(), jac_g, hess_l, vec(x0, n),
+                      vec(lbx, n), vec(ubx, n), vec(lbg, m), vec(ubg, m), tol=tol,
+                      max_iter=int(self.opts.get("ipopt.max_iter", 3000)),
+                      acceptable_tol=float(self.opts.get("ipopt.acceptable_tol", 1e-6)))
+        self.stats_ = {"success": bool(r.success), "iter_count": int(r.iter),
+                       "return_status": "Solve_Succeeded" if r.success else "Maximum_Iterations_Exceeded"}
+        return {"x": DM(r.x), "f": DM(r.f), "g": DM(r.g), "lam_g": DM(r.lam_g), "lam_x": DM(r.lam_x),
+                "lam_p": DM(np.zeros(0 if pv is None else pv.size))}
 
 
 def nlpsol(name, plugin, nlp, opts=None):

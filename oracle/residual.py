@@ -45,8 +45,8 @@ def interpolated_time_grid(t_orig, taus, poly_orders, tau0, tau1):
                            for i in range(len(t_seg) - 1)])
 
 
-def residual_grid_taus(ora, phase, grid_type, p=None, max_grid_points=20):
-    """mpopt.py:1152-1203 (``_MAX_GRID_POINTS`` = 20, :53)."""
+def residual_grid_taus(ora, phase, grid_type, p=None, max_grid_points=15):
+    """mpopt.py:1152-1203 (``_MAX_GRID_POINTS`` = 15, :53; found wrong (20) by running the reference, oracle/refrun)."""
     p = ora.seg_width_params() if p is None else np.asarray(p, dtype=float)
     if grid_type == "fixed":
         n_nodes = max(sum(ora.po) + 2, max_grid_points + 2)

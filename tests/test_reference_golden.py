@@ -157,3 +157,80 @@ def test_cuda_matches_reference_run(libmpx, name):
         return
     assert np.array_equal(hrp, G["hrowptr"]) and np.array_equal(hci, G["hcolind"]), "Hessian pattern"
     assert_close(tr.hess_l_values(G["z"], G["p"], float(G["lam_f"]), G["lam_g"]), G["hvalues"], "hess_l values")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# interpolation / residual path: fixtures from the reference's own residual functions
+
+import make_reference_residual_golden as MRR  # noqa: E402
+
+
+def _split(flat, counts):
+    off = np.concatenate([[0], np.cumsum(counts)])
+    return [flat[off[k]: off[k + 1]] for k in range(len(counts))]
+
+
+@pytest.mark.parametrize("name", sorted(MRR.CASES))
+def test_oracle_residual_path_matches_reference_run(name):
+    from mpopt_b200.problems import REGISTRY
+    from oracle import residual as R
+    from oracle.nlp import OracleNLP
+
+    problem, K, deg, scheme, _ = MRR.CASES[name]
+    G = np.load(os.path.join(GOLD, "refres_" + name + ".npz"))
+    ora = OracleNLP(REGISTRY[problem](), K, deg, scheme)
+    z, p = G["z"], G["p"]
+    for ph in range(int(G["n_phases"])):
+        for grid in MRR.GRIDS:
+            key = f"ph{ph}_{grid}_"
+            taus = R.residual_grid_taus(ora, ph, grid, p)
+            assert [len(t) for t in taus] == G[key + "counts"].tolist(), "points per segment"
+            assert_close(np.concatenate(taus), G[key + "taus"], "target points", 1e-13)
+            taus = _split(G[key + "taus"], G[key + "counts"])
+            Xi, Ui, ti, DXi, DUi = R.interpolate_phase(ora, z, p, ph, taus)
+            for a, k in ((Xi, "xi"), (Ui, "ui"), (ti, "ti"), (DXi, "dxi"), (DUi, "dui")):
+                assert_close(a, G[key + k], k, 1e-12)
+            assert_close(R.dynamics_residuals_phase(ora, z, p, ph, taus)[1], G[key + "res"], "residual", 1e-12)
+            _, ddx, ddu = R.second_derivatives_phase(ora, z, p, ph, taus)
+            assert_close(ddx, G[key + "ddxi"], "ddxi", 1e-11)
+            assert_close(ddu, G[key + "ddui"], "ddui", 1e-11)
+            xint, resx, _ = R.states_from_dynamics_phase(ora, z, p, ph, taus)
+            assert_close(xint, G[key + "xint"], "xint", 1e-12)
+            assert_close(resx, G[key + "res_x"], "res_x", 1e-12)
+
+
+def test_residual_fixtures_come_from_the_reference():
+    from oracle.refrun import run_reference as rr
+
+    if not rr.available():
+        pytest.skip("reference tree not present")
+    name = "sink_K3_p5_LGL"
+    out, G = MRR.run(name), np.load(os.path.join(GOLD, "refres_" + name + ".npz"))
+    assert sorted(out) == sorted(G.files)
+    for k in G.files:
+        assert_close(np.asarray(out[k], float), np.asarray(G[k], float), k, 1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MRR.CASES))
+def test_cuda_residual_path_matches_reference_run(libmpx, name):
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+
+    problem, K, deg, scheme, _ = MRR.CASES[name]
+    G = np.load(os.path.join(GOLD, "refres_" + name + ".npz"))
+    tr = Transcription(REGISTRY[problem](), K, deg, scheme)
+    z, p = G["z"], G["p"]
+    for ph in range(int(G["n_phases"])):
+        for grid in MRR.GRIDS:
+            key = f"ph{ph}_{grid}_"
+            taus = _split(G[key + "taus"], G[key + "counts"])
+            r = tr.residuals(z, p, phase=ph, taus=taus)
+            for k in ("xi", "ui", "ti", "dxi", "dui", "res"):
+                assert_close(r[k], G[key + k], f"{grid} {k}")
+            d2 = tr.second_derivatives(z, p, phase=ph, taus=taus)
+            assert_close(d2["ddxi"], G[key + "ddxi"], f"{grid} ddxi", 1e-9)
+            assert_close(d2["ddui"], G[key + "ddui"], f"{grid} ddui", 1e-9)
+            s = tr.state_residuals(z, p, phase=ph, taus=taus)
+            assert_close(s["xint"], G[key + "xint"], f"{grid} xint")
+            assert_close(s["res_x"], G[key + "res_x"], f"{grid} res_x")
