@@ -2701,6 +2701,10 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
     if (p.adaptive) {
       a.hpart2 = p.d_hpart2.as<double>();
       a.ah_pos = H.ah_pos.as<int64_t>(), a.ah_off = H.ah_off.as<int64_t>();
+      // MPX_TRACE=1: per-segment timeline behind the records of mpx_hess_kernel (one per warp of nodes)
+      const size_t trace_cap = (size_t)MPX_TRACE_RING * p.v2_grid * p.v2_warps, trace_base = (size_t)p.N / 32 + 1;
+      a.ah_trace = (p.d_trace.p && trace_base + (size_t)p.K <= trace_cap)
+                       ? p.d_trace.as<unsigned long long>() + trace_base * MPX_TRACE_SLOTS : nullptr;
       const int dmax = *std::max_element(p.po.begin(), p.po.end());
       for (int par = 0; par < 2; ++par) {
         const int grid = (p.K - par + 1) / 2;
