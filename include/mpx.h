@@ -187,6 +187,10 @@ int mpx_eval_jac_g_packed(mpx_plan* plan, const double* z, const double* p, doub
  *    MPX_TRACE=1 (n_warps records of `slots` 64-bit stamps; out == NULL: only the counts). */
 int mpx_gate(void* stream, double usec);
 int mpx_trace_read(mpx_plan* plan, int64_t* n_warps, int64_t* slots, unsigned long long* out);
+/*    mpx_hess_zero_fill: whether the Hessian of an adaptive plan (mpopt_adaptive's NLP) zero-fills its output before
+ *    the kernels run: -1 not evaluated yet, 0 no (the first evaluation ran on a NaN-filled buffer and every entry of
+ *    the pattern turned out to have a writer), 1 yes.  Always 0 for a plan that is not adaptive. */
+int mpx_hess_zero_fill(const mpx_plan* plan, int* state);
 
 /* -- fused evaluation + all-gather over peer memory (multi-GPU, one process per GPU): every store of the g + jac_g
  *    kernel is issued to this GPU's buffers AND to the same offsets of n_peers peer buffers (other GPUs' allocations

@@ -100,6 +100,7 @@ PROTOTYPES = {
     "mpx_eval_jac_g_packed": (C.c_int, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p]),
     "mpx_gate": (C.c_int, [C.c_void_p, C.c_double]),
     "mpx_trace_read": (C.c_int, [C.c_void_p, c_i64p, c_i64p, C.POINTER(C.c_uint64)]),
+    "mpx_hess_zero_fill": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "mpx_ipopt_eval_f": (C.c_int, [C.c_int, c_f64p, C.c_int, c_f64p, C.c_void_p]),
     "mpx_ipopt_eval_grad_f": (C.c_int, [C.c_int, c_f64p, C.c_int, c_f64p, C.c_void_p]),
     "mpx_ipopt_eval_g": (C.c_int, [C.c_int, c_f64p, C.c_int, C.c_int, c_f64p, C.c_void_p]),

@@ -114,6 +114,14 @@ __global__ void mpx_compact_kernel(const double* __restrict__ full, const int64_
 }
 
 // dynamic fetch: the z- / p-dependent Jacobian entries gathered into a contiguous device buffer (ONE device-to-host copy)
+// how many entries of v are NaN (one-time coverage probe of the adaptive Hessian, see launch_hess)
+__global__ void mpx_count_nan_kernel(const double* __restrict__ v, int64_t n, unsigned long long* count) {
+  unsigned long long c = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += v[i] != v[i];
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
 __global__ void mpx_gather_dyn_kernel(const double* __restrict__ vals, const int32_t* __restrict__ pos,
                                       double* __restrict__ out, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -396,6 +404,7 @@ struct mpx_plan {
   bool p_valid = false;
   // Hessian of the Lagrangian (built on first use): lower triangle, CSR
   bool hess_built = false;
+  int ah_zero_fill = -1;  // adaptive Hessian: 1 = the evaluation needs a zero-filled buffer, 0 = every entry has a writer, -1 = not probed yet
   std::vector<int64_t> h_rowptr, h_colind;
   struct HessPhase {
     DevBuf pos_yy, pos_ay, pos_ty, pos_corner, pos_term, term_assign, part;
@@ -1730,6 +1739,12 @@ extern "C" int mpx_plan_create(const mpx_problem_desc* d, mpx_plan** out) {
 
 // diagnostics: the timeline records of the last MPX_TRACE_RING K2 launches (MPX_TRACE=1 at plan creation), oldest
 // first: n_warps records (= ring x warps per launch) of MPX_TRACE_SLOTS 64-bit stamps. out == NULL: only the count.
+extern "C" int mpx_hess_zero_fill(const mpx_plan* p, int* state) {
+  if (!p || !state) return fail(MPX_EINVAL, "NULL argument");
+  *state = p->adaptive ? p->ah_zero_fill : 0;
+  return MPX_OK;
+}
+
 extern "C" int mpx_trace_read(mpx_plan* p, int64_t* n_warps, int64_t* slots, unsigned long long* out) {
   if (!p) return fail(MPX_EINVAL, "NULL plan");
   const int64_t nw = p->d_trace.p ? (int64_t)MPX_TRACE_RING * p->v2_grid * p->v2_warps : 0;
@@ -2683,8 +2698,22 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
   bool need_sig = false;  // sigma only enters through explicit time dependence
   for (auto& L : p.ph) need_sig |= L.uses_t || L.cost_t;
   if (need_sig) scan_widths(p, d_z, d_p, st);
-  if (p.adaptive)  // the widths' contributions are ADDED on top of the node-local part (mpx_adapt_hess_kernel)
-    CUDA_TRY(cudaMemsetAsync(d_vals, 0, p.h_colind.size() * sizeof(double), st));
+  // The widths' contributions are ADDED on top of the node-local part (mpx_adapt_hess_kernel), so the buffer used to be
+  // zero-filled first: 179 MB = 28 us at the headline size, although every entry of the pattern normally has a writer
+  // (plain store) ahead of whatever is added to it.  Probed once per plan: the first evaluation runs on a buffer filled
+  // with NaN; if no NaN survives, nothing leans on the initial content and the fill is skipped from then on.
+  bool probing = false;
+  if (p.adaptive) {
+    if (p.ah_zero_fill < 0) {
+      const char* ze = getenv("MPX_AHESS_ZERO");
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      CUDA_TRY(cudaStreamIsCapturing(st, &cs));
+      if (ze && atoi(ze) != 0) p.ah_zero_fill = 1;
+      else if (cs == cudaStreamCaptureStatusNone) probing = true;
+    }
+    if (probing) CUDA_TRY(cudaMemsetAsync(d_vals, 0xFF, p.h_colind.size() * sizeof(double), st));
+    else if (p.ah_zero_fill != 0) CUDA_TRY(cudaMemsetAsync(d_vals, 0, p.h_colind.size() * sizeof(double), st));
+  }
   for (int ph = 0; ph < p.P; ++ph) {
     MpxPhaseArgs a = p.args[ph];
     auto& H = p.hess_ph[ph];
@@ -2716,6 +2745,17 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
       CUDA_TRY(p.prog->phases[ph]->adapt_hess_final(a, st));
       ++p.launches;
     }
+  }
+  if (probing) {
+    unsigned long long* cnt = reinterpret_cast<unsigned long long*>(p.d_hpart2.p);  // free once the corner sum has run
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+    mpx_count_nan_kernel<<<592, 256, 0, st>>>(d_vals, (int64_t)p.h_colind.size(), cnt);
+    CUDA_TRY(cudaGetLastError());
+    unsigned long long h = 0;
+    CUDA_TRY(cudaMemcpyAsync(&h, cnt, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    p.ah_zero_fill = h ? 1 : 0;
+    return launch_hess(p, d_z, d_p, lam_f, d_lam, d_vals, st);  // the evaluation proper
   }
   return MPX_OK;
 }

@@ -228,6 +228,14 @@ class Transcription:
         _lib.check(self._L.mpx_eval_hess_l(self._plan, _lib.ptr(z), _lib.ptr(p), float(lam_f), _lib.ptr(lam), _lib.ptr(out)))
         return out
 
+    @property
+    def hess_zero_fill(self):
+        """Adaptive plans: -1 before the first Hessian evaluation, 0 when it runs without zero-filling its output (every
+        entry of the pattern has a writer; probed once on a NaN-filled buffer), 1 when it zero-fills."""
+        st = C.c_int(0)
+        _lib.check(self._L.mpx_hess_zero_fill(self._plan, C.byref(st)))
+        return st.value
+
     def hess_l(self, z, p=None, lam_f=1.0, lam_g=None):
         """Lower triangle of the Hessian of ``lam_f * f + lam_g . g`` as scipy.sparse.csr_matrix (CasADi's nlp_hess_l)."""
         import scipy.sparse as sp

@@ -160,6 +160,12 @@ def test_adaptive_hessian_matches_oracle(libmpx, problem, K, po, scheme, mid):
     assert diff.max() <= 1e-10 * max(1.0, abs(H0).max())
     # evaluating twice gives the same bits (the += accumulation is ordered)
     assert np.array_equal(tr.hess_l_values(z, None, 0.7, lam), tr.hess_l_values(z, None, 0.7, lam))
+    # the first evaluation probed (on a NaN-filled buffer) whether every entry of the pattern has a writer; none of
+    # these problems needs the zero fill, and nothing of an earlier evaluation survives in the device buffer
+    assert tr.hess_zero_fill == 0
+    z2 = z * 0.9 + 0.01
+    lam2 = np.random.default_rng(10).uniform(-1, 1, tr.n_g)
+    assert_close(tr.hess_l_values(z2, None, 0.3, lam2), hess_l(ora, z2, None, 0.3, lam2).data, "hess_l values, second point")
 
 
 # ---------------------------------------------------------------------------- the reference's adaptive tests
