@@ -410,6 +410,7 @@ struct mpx_plan {
     DevBuf pos_yy, pos_ay, pos_ty, pos_corner, pos_term, term_assign, part;
     MpxHessLin lin;  // affine positions of the interior nodes' entries, passed to the node kernel by value
     DevBuf ah_pos, ah_off;  // adaptive NLP: positions of what a segment adds (mpx_adapt_hess_kernel), [K + 1] offsets
+    DevBuf ah_sync;         // [3 + K] queue, epoch and per-segment flags of the persistent launch
     int blocks = 0, n_corner = 0;
   };
   std::vector<HessPhase> hess_ph;
@@ -687,7 +688,8 @@ struct MpxRtPhase final : MpxPhaseKernels {
     const int n1 = dmax + 1, ny = nx_ + nu_, nv = ny + na_, nr = 1 + nv + nv * (nv + 1) / 2;
     const size_t dbl = 2 * (size_t)MpxTab::pad2(dmax * n1) + MpxTab::pad2(n1) + MpxTab::pad2(ny * n1) + MpxTab::pad2(ny * dmax) +
                        MpxTab::pad2(dmax * nr) + MpxTab::pad2(n1 * (1 + nv)) + MpxTab::pad2(nx_ * dmax) + 4 +
-                       (size_t)(1 + MPX_THREADS / 32) * n1 * mpx_ahess_stride(dmax) + (size_t)(3 * ny + nv * (nv + 1) / 2) * n1 + na_ + 3;
+                       (size_t)(1 + MPX_THREADS / 32) * n1 * mpx_ahess_stride(dmax) + (size_t)(3 * ny + nv * (nv + 1) / 2) * n1 + na_ + 3 +
+                       (size_t)(2 * ny + nv * (nv + 1) / 2) * n1;  // + the prefetched old values (mpx_adapt_hess_smem_doubles)
     return go(f_ahess[0], a, grid, MPX_THREADS, dbl * sizeof(double), st);
   }
   cudaError_t adapt_hess_final(const MpxPhaseArgs& a, cudaStream_t st) const override { return go(f_ahess[1], a, 1, 64, 0, st); }
@@ -2684,6 +2686,9 @@ int build_hessian(mpx_plan& p) {
       off[(size_t)p.K] = (int64_t)pos.size();
       CUDA_TRY(upload(p.hess_ph[ph].ah_pos, pos.data(), pos.size() * sizeof(int64_t)));
       CUDA_TRY(upload(p.hess_ph[ph].ah_off, off.data(), off.size() * sizeof(int64_t)));
+      std::vector<unsigned int> sync0((size_t)p.K + 3, 0u);
+      sync0[2] = 1u;  // epoch of the first launch (flags start at 0)
+      CUDA_TRY(upload(p.hess_ph[ph].ah_sync, sync0.data(), sync0.size() * sizeof(unsigned int)));
     }
     CUDA_TRY(p.d_hpart2.ensure((size_t)p.K * (3 + 2 * na + na * (na + 1) / 2) * sizeof(double)));
   }
@@ -2735,12 +2740,21 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
       a.ah_trace = (p.d_trace.p && trace_base + (size_t)p.K <= trace_cap)
                        ? p.d_trace.as<unsigned long long>() + trace_base * MPX_TRACE_SLOTS : nullptr;
       const int dmax = *std::max_element(p.po.begin(), p.po.end());
-      for (int par = 0; par < 2; ++par) {
-        const int grid = (p.K - par + 1) / 2;
-        if (grid <= 0) continue;
-        a.ah_parity = par;
-        CUDA_TRY(p.prog->phases[ph]->adapt_hess(a, grid, dmax, st));
+      static const bool persist = !(getenv("MPX_AHESS_PERSIST") && atoi(getenv("MPX_AHESS_PERSIST")) == 0);
+      if (persist) {  // one launch: persistent CTAs, even segments first, flags at the shared nodes (see the kernel)
+        a.ah_parity = -1;
+        a.ah_sync = H.ah_sync.as<unsigned int>();
+        if (p.num_sms <= 0) CUDA_TRY(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, p.device));
+        CUDA_TRY(p.prog->phases[ph]->adapt_hess(a, std::min(p.K, 4 * std::max(1, p.num_sms)), dmax, st));
         ++p.launches;
+      } else {
+        for (int par = 0; par < 2; ++par) {
+          const int grid = (p.K - par + 1) / 2;
+          if (grid <= 0) continue;
+          a.ah_parity = par;
+          CUDA_TRY(p.prog->phases[ph]->adapt_hess(a, grid, dmax, st));
+          ++p.launches;
+        }
       }
       CUDA_TRY(p.prog->phases[ph]->adapt_hess_final(a, st));
       ++p.launches;

@@ -46,6 +46,7 @@ T = buf.reshape(-1, sl.value)[base: base + K].astype(np.int64)
 ghz = 1.965
 q = lambda a: [round(float(x), 2) for x in np.percentile(a, [0, 10, 50, 90, 100])]
 us = lambda a, b: (T[:, b] - T[:, a]) / ghz / 1e3
+print("all segments: span us", (T[:, 10].max() - T[:, 0].min()) / 1e3, " odd segments start (global us)", q((T[1::2, 0] - T[:, 0].min()) / 1e3))
 for par in (0, 1):
     P = T[par::2]
     g0 = P[:, 0].min()
@@ -60,5 +61,14 @@ print("(b) scalars (6->7)                   ", q(us(6, 7)))
 print("(c) blocks, warp 0's share (7->8)    ", q(us(7, 8)))
 print("diagonal pass (8->9)                 ", q(us(8, 9)))
 print("segment total (1->9)                 ", q(us(1, 9)))
+cta = T[:, 14]
+gaps = []
+for c in np.unique(cta):
+    R = T[cta == c]
+    R = R[np.argsort(R[:, 0])]
+    gaps.extend(((R[1:, 0] - R[:-1, 10]) / 1e3).tolist())
+if gaps:
+    print("gap between a CTA's segments, global us (end stamp -> next start stamp)", q(np.array(gaps)), " segments per CTA", q(np.bincount(cta.astype(int))))
+print("segment, global timer (0->10) us     ", q((T[:, 10] - T[:, 0]) / 1e3))
 sm = T[:, 15]
 print("segments per SM", q(np.bincount(sm.astype(int))[np.bincount(sm.astype(int)) > 0]))
