@@ -226,13 +226,26 @@ struct MpxAotPhase final : MpxPhaseKernels {
     if (suffix) mpx_adapt_grad_suffix<PH><<<1, 32, 0, st>>>(a);  // time-dependent running cost only
     return cudaGetLastError();
   }
-  cudaError_t adapt_hess(const MpxPhaseArgs& a, int grid, int dmax, cudaStream_t st) const override {
+  template <int DEG>
+  static cudaError_t launch_ah(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) {
     static bool done = false;
-    const size_t smem = (size_t)mpx_adapt_hess_smem_doubles<PH>(dmax) * sizeof(double);
-    cudaError_t e = allow_smem(mpx_adapt_hess_kernel<PH>, smem, done);
+    cudaError_t e = allow_smem(mpx_adapt_hess_kernel<PH, DEG>, smem, done);
     if (e != cudaSuccess) return e;
-    mpx_adapt_hess_kernel<PH><<<grid, MPX_THREADS, smem, st>>>(a);
+    mpx_adapt_hess_kernel<PH, DEG><<<grid, MPX_THREADS, smem, st>>>(a);
     return cudaGetLastError();
+  }
+  template <int D0, int... REST>
+  static cudaError_t pick_ah(int deg, const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) {
+    if constexpr (sizeof...(REST) == 0) {
+      return launch_ah<D0>(a, grid, smem, st);  // the list ends with 0 = generic
+    } else {
+      if (deg == D0) return launch_ah<D0>(a, grid, smem, st);
+      return pick_ah<REST...>(deg, a, grid, smem, st);
+    }
+  }
+  cudaError_t adapt_hess(const MpxPhaseArgs& a, int grid, int dmax, cudaStream_t st) const override {
+    const size_t smem = (size_t)mpx_adapt_hess_smem_doubles<PH>(dmax) * sizeof(double);
+    return pick_ah<DEGS..., 0>(a.uniform_deg > 0 ? a.uniform_deg : 0, a, grid, smem, st);  // degree-specialised when the plan is uniform
   }
   cudaError_t adapt_hess_final(const MpxPhaseArgs& a, cudaStream_t st) const override {
     mpx_adapt_hess_final<PH><<<1, 64, 0, st>>>(a);

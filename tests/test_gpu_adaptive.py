@@ -125,6 +125,8 @@ HESS_CASES = [("moon_lander", 3, 3, "LGR", True), ("moon_lander", 4, [4, 2, 3, 5
               ("synthetic_6_3", 2, 3, "LGR", True), ("synthetic_6_3", 5, 6, "LGR", False),
               ("van_der_pol", 3, 5, "LGR", True), ("two_phase_schwartz", 2, 4, "LGR", True),
               ("robot_arm", 2, 4, "LGR", True),
+              # uniform degrees with a degree-specialised instance of mpx_adapt_hess_kernel (problems.py::AOT_DEGREES)
+              ("synthetic_6_3", 3, 15, "LGR", True), ("moon_lander", 4, 15, "LGL", True), ("two_phase_schwartz", 3, 10, "CGL", True),
               # degrees above 15: the dense blocks leave the tensor-core path for the per-warp product tiles
               ("hyper_sensitive", 2, 20, "LGR", True), ("van_der_pol", 3, [18, 4, 17], "LGL", True),
               ("synthetic_6_3", 2, [16, 15], "CGL", True)]
