@@ -411,6 +411,7 @@ struct mpx_plan {
     MpxHessLin lin;  // affine positions of the interior nodes' entries, passed to the node kernel by value
     DevBuf ah_pos, ah_off;  // adaptive NLP: positions of what a segment adds (mpx_adapt_hess_kernel), [K + 1] offsets
     DevBuf ah_sync;         // [3 + K] queue, epoch and per-segment flags of the persistent launch
+    DevBuf hnl;             // [NRH][N] staging of the node-local block-diagonal entries (MpxPhaseArgs::hnl); empty: off
     int blocks = 0, n_corner = 0;
   };
   std::vector<HessPhase> hess_ph;
@@ -2686,6 +2687,16 @@ int build_hessian(mpx_plan& p) {
       off[(size_t)p.K] = (int64_t)pos.size();
       CUDA_TRY(upload(p.hess_ph[ph].ah_pos, pos.data(), pos.size() * sizeof(int64_t)));
       CUDA_TRY(upload(p.hess_ph[ph].ah_off, off.data(), off.size() * sizeof(int64_t)));
+      // staging of the node-local entries under the block diagonals: only if every block pair is also a pair of the
+      // node Lagrangian (it is, by construction: the Lagrangian contains every f_s with its own multiplier)
+      bool stage = !(getenv("MPX_AHESS_STAGE") && atoi(getenv("MPX_AHESS_STAGE")) == 0) && !p.hess_ph[ph].lin.rows &&
+                   p.args[ph].ad_res;  // without the residual rows nothing would pick the staged entries up
+      size_t n_blocks = 0;
+      for (auto& ab : rh) {
+        if (ab.first < ny && !L.pat_hw[(size_t)ab.first * NW + ab.second]) stage = false;
+        ++n_blocks;
+      }
+      if (stage && n_blocks) CUDA_TRY(p.hess_ph[ph].hnl.ensure(n_blocks * (size_t)N * sizeof(double)));
       std::vector<unsigned int> sync0((size_t)p.K + 3, 0u);
       sync0[2] = 1u;  // epoch of the first launch (flags start at 0)
       CUDA_TRY(upload(p.hess_ph[ph].ah_sync, sync0.data(), sync0.size() * sizeof(unsigned int)));
@@ -2729,6 +2740,7 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
     a.hp_corner = H.pos_corner.as<int64_t>(), a.hp_term = H.pos_term.as<int64_t>();
     a.hp_term_assign = H.term_assign.as<int32_t>();
     a.hvals = d_vals, a.hpart = H.part.as<double>(), a.h_blocks = H.blocks;
+    a.hnl = p.adaptive && H.hnl.p ? H.hnl.as<double>() : nullptr;
     a.trace = p.d_trace.p ? p.d_trace.as<unsigned long long>() : nullptr;  // MPX_TRACE=1: per-warp timeline stamps
     CUDA_TRY(p.prog->phases[ph]->hess(a, H.lin, H.blocks, st));
     p.launches += a.ticket ? 1 : 2;
