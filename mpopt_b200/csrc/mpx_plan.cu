@@ -411,6 +411,7 @@ struct mpx_plan {
     MpxHessLin lin;  // affine positions of the interior nodes' entries, passed to the node kernel by value
     DevBuf ah_pos, ah_off;  // adaptive NLP: positions of what a segment adds (mpx_adapt_hess_kernel), [K + 1] offsets
     DevBuf ah_sync;         // [3 + K] queue, epoch and per-segment flags of the persistent launch
+    bool ah_persist = true; // one persistent launch (MPX_AHESS_PERSIST=0 at plan creation: one launch per segment parity)
     DevBuf hnl;             // [NRH][N] staging of the node-local block-diagonal entries (MpxPhaseArgs::hnl); empty: off
     int blocks = 0, n_corner = 0;
   };
@@ -2697,6 +2698,7 @@ int build_hessian(mpx_plan& p) {
         ++n_blocks;
       }
       if (stage && n_blocks) CUDA_TRY(p.hess_ph[ph].hnl.ensure(n_blocks * (size_t)N * sizeof(double)));
+      p.hess_ph[ph].ah_persist = !(getenv("MPX_AHESS_PERSIST") && atoi(getenv("MPX_AHESS_PERSIST")) == 0);
       std::vector<unsigned int> sync0((size_t)p.K + 3, 0u);
       sync0[2] = 1u;  // epoch of the first launch (flags start at 0)
       CUDA_TRY(upload(p.hess_ph[ph].ah_sync, sync0.data(), sync0.size() * sizeof(unsigned int)));
@@ -2752,8 +2754,7 @@ int launch_hess(mpx_plan& p, const double* d_z, const double* d_p, double lam_f,
       a.ah_trace = (p.d_trace.p && trace_base + (size_t)p.K <= trace_cap)
                        ? p.d_trace.as<unsigned long long>() + trace_base * MPX_TRACE_SLOTS : nullptr;
       const int dmax = *std::max_element(p.po.begin(), p.po.end());
-      static const bool persist = !(getenv("MPX_AHESS_PERSIST") && atoi(getenv("MPX_AHESS_PERSIST")) == 0);
-      if (persist) {  // one launch: persistent CTAs, even segments first, flags at the shared nodes (see the kernel)
+      if (H.ah_persist) {  // one launch: persistent CTAs, even segments first, flags at the shared nodes (see the kernel)
         a.ah_parity = -1;
         a.ah_sync = H.ah_sync.as<unsigned int>();
         if (p.num_sms <= 0) CUDA_TRY(cudaDeviceGetAttribute(&p.num_sms, cudaDevAttrMultiProcessorCount, p.device));

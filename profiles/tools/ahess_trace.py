@@ -69,6 +69,8 @@ for c in np.unique(cta):
     gaps.extend(((R[1:, 0] - R[:-1, 10]) / 1e3).tolist())
 if gaps:
     print("gap between a CTA's segments, global us (end stamp -> next start stamp)", q(np.array(gaps)), " segments per CTA", q(np.bincount(cta.astype(int))))
+print("end of work -> index stored (10->11), end barrier (11->13) us", q((T[:, 11] - T[:, 10]) / 1e3), q((T[:, 13] - T[:, 11]) / 1e3))
+print("loop top -> start stamp (12->0): even, odd us", q((T[0::2, 0] - T[0::2, 12]) / 1e3), q((T[1::2, 0] - T[1::2, 12]) / 1e3))
 print("segment, global timer (0->10) us     ", q((T[:, 10] - T[:, 0]) / 1e3))
 sm = T[:, 15]
 print("segments per SM", q(np.bincount(sm.astype(int))[np.bincount(sm.astype(int)) > 0]))

@@ -170,6 +170,38 @@ def test_adaptive_hessian_matches_oracle(libmpx, problem, K, po, scheme, mid):
     assert_close(tr.hess_l_values(z2, None, 0.3, lam2), hess_l(ora, z2, None, 0.3, lam2).data, "hess_l values, second point")
 
 
+@pytest.mark.parametrize("problem,K,po,scheme", [("synthetic_6_3", 7, 15, "LGR"), ("moon_lander", 6, [4, 2, 3, 5, 4, 3], "LGL"),
+                                                 ("two_phase_schwartz", 4, 10, "CGL")])
+def test_adaptive_hessian_launch_variants_agree_bit_for_bit(libmpx, monkeypatch, problem, K, po, scheme):
+    """The shipped path (ONE persistent launch with flags at the shared nodes, node-local block diagonals staged and
+    written with their runs) against the plainer ones it replaced: one launch per segment parity (MPX_AHESS_PERSIST=0),
+    node-local entries stored by mpx_hess_kernel and added to afterwards (MPX_AHESS_STAGE=0), the zero-filled buffer
+    (MPX_AHESS_ZERO=1).  Every entry is the same sum in the same order: the bits must agree."""
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.problems import REGISTRY
+    from oracle.adaptive import OracleAdaptiveNLP
+
+    ocp = REGISTRY[problem]()
+    ora = OracleAdaptiveNLP(ocp, K, po, scheme)
+    z = _point(ora, problem)
+    lam = np.random.default_rng(5).uniform(-1, 1, ora.n_g)
+    vals = {}
+    for name, env in (("shipped", {}), ("two launches", {"MPX_AHESS_PERSIST": "0"}), ("no staging", {"MPX_AHESS_STAGE": "0"}),
+                      ("plain", {"MPX_AHESS_PERSIST": "0", "MPX_AHESS_STAGE": "0", "MPX_AHESS_ZERO": "1"})):
+        for k_ in ("MPX_AHESS_PERSIST", "MPX_AHESS_STAGE", "MPX_AHESS_ZERO"):
+            monkeypatch.delenv(k_, raising=False)
+        for k_, v_ in env.items():
+            monkeypatch.setenv(k_, v_)
+        tr = Transcription(ocp, K, po, scheme, adaptive=True)
+        tr.hess_structure()
+        vals[name] = [tr.hess_l_values(z, None, 0.7, lam).copy() for _ in range(3)]  # graph-free repeats: flags / epochs advance
+        assert tr.hess_zero_fill == (1 if env.get("MPX_AHESS_ZERO") else 0)
+        del tr
+    for name, reps in vals.items():
+        for r in reps:
+            assert np.array_equal(r, vals["shipped"][0]), name
+
+
 # ---------------------------------------------------------------------------- the reference's adaptive tests
 @pytest.fixture(scope="module")
 def mp(libmpx):
