@@ -34,6 +34,10 @@ host_us, graph_us = time_call(fn, stream, n=20, warm=4)
 nbytes = 8 * (tr.n_z + tr.n_g + nh)
 print(json.dumps({"evaluator": "hess_l of the adaptive NLP", "K": K, "us": round(graph_us or host_us, 2), "host_issued_us": round(host_us, 2),
                   "nnz_hess_lower": nh, "algorithmic_MB": round(nbytes / 1e6, 1), "GBs": round(nbytes / (graph_us or host_us) / 1e3, 1)}))
+after_graph = hv.clone()
+fn(); torch.cuda.synchronize()
+print(json.dumps({"graph replays leave the same bits as a plain call": bool(torch.equal(after_graph, hv)),
+                  "zero_fill": tr.hess_zero_fill}))
 if os.environ.get("MPX_TRACE") != "1":
     sys.exit(0)
 fn(); torch.cuda.synchronize()
