@@ -61,3 +61,23 @@ def test_reference_on_the_stand_in_reproduces_its_stored_optima():
         assert mpo.nlp_solver.stats()["success"], (problem, scheme)
         gap = abs(float(sol["f"]) - stored) / abs(stored)
         assert gap <= rtol, f"{problem} {scheme} ({where}): {float(sol['f'])!r} vs stored {stored!r}: {gap:.2e}"
+
+
+def test_reference_itself_fails_on_the_schemes_this_package_does_not_offer():
+    """`LG` and the equally-spaced fallback for unknown scheme names (mpopt.py:4157-4205) are not offered here.  Run on the
+    stand-in, the reference's own transcription breaks on both: they return `degree` nodes where every other scheme
+    returns `degree + 1`, and `create_nlp()` indexes past the end of the node array."""
+    from oracle.refrun import run_reference as rr
+
+    if not rr.available():
+        pytest.skip("reference tree not present")
+    from mpopt_b200.problems import REGISTRY
+
+    ref = rr.load_reference()
+    for scheme in ("LG", "no-such-scheme"):
+        with pytest.raises(IndexError):
+            rr.ReferenceNLP(ref, rr.reference_ocp(ref, REGISTRY["moon_lander"]), 2, 3, scheme)
+    import mpopt_b200.nlp as nlp
+
+    with pytest.raises(ValueError):
+        nlp.Transcription(REGISTRY["moon_lander"](), 2, 3, "LG")
