@@ -170,6 +170,37 @@ def test_adaptive_hessian_matches_oracle(libmpx, problem, K, po, scheme, mid):
     assert_close(tr.hess_l_values(z2, None, 0.3, lam2), hess_l(ora, z2, None, 0.3, lam2).data, "hess_l values, second point")
 
 
+@pytest.mark.parametrize("po", [4, [3, 5, 2, 4, 6], 17])
+def test_adaptive_hessian_runtime_compiled_program(libmpx, po):
+    """The Hessian kernels of an unregistered problem come out of NVRTC (generic-degree instance, the run-time launcher
+    sizes the shared memory itself): same checks as the ahead-of-time programs."""
+    from mpopt_b200 import ca
+    from mpopt_b200.nlp import Transcription
+    from mpopt_b200.ocp import OCP
+    from oracle.adaptive import OracleAdaptiveNLP
+    from oracle.hessian import hess_l
+
+    ocp = OCP(n_states=2, n_controls=1)
+    ocp.dynamics[0] = lambda x, u, t: [x[1] * ca.cos(0.37 * x[0]), u[0] - 0.21 * x[0] * x[1] * u[0]]
+    ocp.running_costs[0] = lambda x, u, t: u[0] * u[0] + 0.13 * x[0] * x[0] * x[1]
+    ocp.terminal_costs[0] = lambda xf, tf, x0, t0: xf[0] * xf[1] + tf * xf[0]
+    ocp.lbu[0], ocp.ubu[0] = -1, 1
+    ocp.validate()
+    K = 5 if isinstance(po, list) else 3
+    tr = Transcription(ocp, K, po, "LGL", adaptive=True)
+    ora = OracleAdaptiveNLP(ocp, K, po, "LGL")
+    assert tr.program_origin.startswith("nvrtc:")
+    z = _point(ora, "x")
+    lam = np.random.default_rng(3).uniform(-1, 1, tr.n_g)
+    H = hess_l(ora, z, None, 0.6, lam)
+    rp, ci = tr.hess_structure()
+    assert np.array_equal(rp, H.indptr) and np.array_equal(ci, H.indices)
+    assert_close(tr.hess_l_values(z, None, 0.6, lam), H.data, "hess_l values")
+    assert tr.hess_zero_fill == 0
+    z2 = z * 0.8 - 0.02
+    assert_close(tr.hess_l_values(z2, None, 0.6, lam), hess_l(ora, z2, None, 0.6, lam).data, "hess_l values, second point")
+
+
 @pytest.mark.parametrize("problem,K,po,scheme", [("synthetic_6_3", 7, 15, "LGR"), ("moon_lander", 6, [4, 2, 3, 5, 4, 3], "LGL"),
                                                  ("two_phase_schwartz", 4, 10, "CGL")])
 def test_adaptive_hessian_launch_variants_agree_bit_for_bit(libmpx, monkeypatch, problem, K, po, scheme):
