@@ -209,17 +209,30 @@ struct MpxAotPhase final : MpxPhaseKernels {
     if (!a.ticket) mpx_hess_final<PH><<<1, MPX_HESS_FINAL_THREADS, 0, st>>>(a);  // else done by the node kernel's last CTA
     return cudaGetLastError();
   }
-  cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
+  template <int DEG>
+  static cudaError_t launch_ad(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) {
     static bool d0 = false, d1 = false;
     cudaError_t e;
     if (a.ad_jac) {
-      if ((e = allow_smem(mpx_adapt_kernel<PH, true>, smem, d1)) != cudaSuccess) return e;
-      mpx_adapt_kernel<PH, true><<<grid, MPX_THREADS, smem, st>>>(a);
+      if ((e = allow_smem(mpx_adapt_kernel<PH, true, DEG>, smem, d1)) != cudaSuccess) return e;
+      mpx_adapt_kernel<PH, true, DEG><<<grid, MPX_THREADS, smem, st>>>(a);
     } else {  // g only: a separate instance, so that the row-assembly code does not set its register count
-      if ((e = allow_smem(mpx_adapt_kernel<PH, false>, smem, d0)) != cudaSuccess) return e;
-      mpx_adapt_kernel<PH, false><<<grid, MPX_THREADS, smem, st>>>(a);
+      if ((e = allow_smem(mpx_adapt_kernel<PH, false, DEG>, smem, d0)) != cudaSuccess) return e;
+      mpx_adapt_kernel<PH, false, DEG><<<grid, MPX_THREADS, smem, st>>>(a);
     }
     return cudaGetLastError();
+  }
+  template <int D0, int... REST>
+  static cudaError_t pick_ad(int deg, const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) {
+    if constexpr (sizeof...(REST) == 0) {
+      return launch_ad<D0>(a, grid, smem, st);  // the list ends with 0 = generic
+    } else {
+      if (deg == D0) return launch_ad<D0>(a, grid, smem, st);
+      return pick_ad<REST...>(deg, a, grid, smem, st);
+    }
+  }
+  cudaError_t adapt(const MpxPhaseArgs& a, int grid, size_t smem, cudaStream_t st) const override {
+    return pick_ad<DEGS..., 0>(a.uniform_deg > 0 ? a.uniform_deg : 0, a, grid, smem, st);
   }
   cudaError_t adapt_grad(const MpxPhaseArgs& a, int grid, bool suffix, cudaStream_t st) const override {
     mpx_adapt_grad_kernel<PH><<<grid, MPX_THREADS, 0, st>>>(a);
