@@ -691,7 +691,8 @@ struct MpxRtPhase final : MpxPhaseKernels {
     const size_t dbl = 2 * (size_t)MpxTab::pad2(dmax * n1) + MpxTab::pad2(n1) + MpxTab::pad2(ny * n1) + MpxTab::pad2(ny * dmax) +
                        MpxTab::pad2(dmax * nr) + MpxTab::pad2(n1 * (1 + nv)) + MpxTab::pad2(nx_ * dmax) + 4 +
                        (size_t)(1 + MPX_THREADS / 32) * n1 * mpx_ahess_stride(dmax) + (size_t)(3 * ny + nv * (nv + 1) / 2) * n1 + na_ + 3 +
-                       (size_t)(2 * ny + nv * (nv + 1) / 2) * n1;  // + the prefetched old values (mpx_adapt_hess_smem_doubles)
+                       (size_t)(2 * ny + nv * (nv + 1) / 2) * n1 +  // + the prefetched old values (mpx_adapt_hess_smem_doubles)
+                       (size_t)(3 * ny + nv * (nv + 1) / 2) * n1 + na_ + 3 + MpxTab::pad2(ny * n1) + MpxTab::pad2(nx_ * dmax);
     return go(f_ahess[0], a, grid, MPX_THREADS, dbl * sizeof(double), st);
   }
   cudaError_t adapt_hess_final(const MpxPhaseArgs& a, cudaStream_t st) const override { return go(f_ahess[1], a, 1, 64, 0, st); }
