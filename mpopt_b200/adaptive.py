@@ -296,6 +296,13 @@ class mpopt_adaptive(mpopt):
             self._variables_created = True
         return self._tr
 
+    def _solution_widths(self, z):
+        """The widths are decision variables of this NLP: the trajectories of a solution are laid out on ITS widths
+        (mpopt.py:3248-3273 evaluates the time grid from Z and ignores the parameter), not on those of the last solve."""
+        L, K = self.transcription.layout, self.n_segments
+        z = np.asarray(z, dtype=float).reshape(-1)
+        return np.concatenate([z[L.colW(ph, 0): L.colW(ph, 0) + K] for ph in range(self._ocp.n_phases)])
+
     def get_nlp_constrains_for_segment_widths(self, phase: int = 0):
         """(SW, SWmin, SWmax): row indices and bounds of the width block of one phase (mpopt.py:3034-3136)."""
         tr = self.transcription

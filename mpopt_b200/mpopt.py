@@ -136,6 +136,11 @@ class mpopt:
             sw = [1.0 / self.n_segments] * (self.n_segments * self._ocp.n_phases)
         return np.asarray(sw, dtype=float)
 
+    def _solution_widths(self, z):
+        """Width fractions the time grid of solution vector ``z`` is built with: here the parameters of the last solve
+        (mpopt.py:873-896 evaluates the trajectories with ``_nlp_sw_params``); ``mpopt_adaptive`` reads them out of ``z``."""
+        return self._current_widths()
+
     # ------------------------------------------------------------------ solver
     def create_solver(self, solver: str = "ipopt", options={}):
         nlp_problem, self.nlp_bounds = self.create_nlp()
@@ -385,7 +390,7 @@ class post_process:
         U = z[off + o.nx * N:off + (o.nx + o.nu) * N].reshape(o.nu, N).T
         T0, TF = z[L.colT0(phase)] / o.scale_t, z[L.colTF(phase)] / o.scale_t
         A = z[L.colT0(phase) + 2:L.colT0(phase) + 2 + o.na]
-        w = (mpo._current_widths() if widths is None else np.asarray(widths, float))[phase * tr.K:(phase + 1) * tr.K]
+        w = (mpo._solution_widths(z) if widths is None else np.asarray(widths, float))[phase * tr.K:(phase + 1) * tr.K]
         delta = tr.tau1 - tr.tau0
         t = np.empty(N)
         t[0], acc = T0, T0

@@ -308,6 +308,18 @@ def test_moon_lander_mpopt_adaptive_solve(mp):
     assert abs(sol["f"] - 8.2477) < 0.2
     x, u, t, _ = post.get_data()
     assert abs(x[0, 0] - 10.0) < 1e-9 and abs(x[-1, 0]) < 1e-5
+    # the trajectories of ANOTHER solution vector are laid out on that vector's own widths, not on those of the last
+    # solve (the reference evaluates the time grid from Z: mpopt.py:3248-3273)
+    L = mpo.transcription.layout
+    z2 = np.array(sol["x"], dtype=float).reshape(-1).copy()
+    w2 = np.array([0.5, 0.2, 0.3])
+    z2[L.colW(0, 0): L.colW(0, 0) + 3] = w2
+    post2 = mpo.process_results({**sol, "x": z2}, plot=False)
+    _, _, t2, _ = post2.get_data()
+    t0, tf = z2[L.colT0(0)], z2[L.colTF(0)]
+    ends = t2.ravel()[[3, 6, 9]]
+    assert np.allclose(ends, t0 + (tf - t0) * np.cumsum(w2), rtol=0, atol=1e-12)
+    assert np.allclose(mpo._nlp_sw_params, sw)  # the last solve's widths are untouched
 
 
 def test_hyper_sensitive_mpopt_adaptive_structure(mp):
