@@ -234,3 +234,35 @@ def test_cuda_residual_path_matches_reference_run(libmpx, name):
             s = tr.state_residuals(z, p, phase=ph, taus=taus)
             assert_close(s["xint"], G[key + "xint"], f"{grid} xint")
             assert_close(s["res_x"], G[key + "res_x"], f"{grid} res_x")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's own solve() against mp.solve of this package
+
+def _solutions():
+    import json
+
+    with open(os.path.join(GOLD, "ref_solutions.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rec", _solutions(), ids=lambda r: f"{r['cls']}-{r['problem']}-{r['n_segments']}x{r['poly_orders']}-{r['scheme']}")
+def test_mp_solve_matches_reference_solve(libmpx, rec):
+    """tests/golden/ref_solutions.json: optima of the UNMODIFIED reference's ``mpopt(...).solve()`` /
+    ``mpopt_adaptive(...).solve()`` (run on the stand-ins of oracle/refrun; BASELINE.json's config 1 is the first record).
+    The same call through ``mpopt_b200.mp`` -- GPU evaluators behind the same interior-point method -- must land on the
+    same optimum."""
+    from mpopt_b200 import mp
+    from mpopt_b200.problems import REGISTRY
+
+    assert rec["success"]
+    mp.mpopt._MUTE_ = True
+    mpo = getattr(mp, rec["cls"])(REGISTRY[rec["problem"]](), rec["n_segments"], rec["poly_orders"], rec["scheme"])
+    sol = mpo.solve(nlp_solver_options={"ipopt.tol": 1e-10})
+    f = float(sol["f"])
+    if abs(rec["f"]) < 1e-12:
+        assert abs(f) < 1e-10
+    else:
+        rtol = 1e-6 if rec["cls"] == "mpopt" else 1e-4  # the widths-as-variables NLP is not convex: same basin, looser
+        assert abs(f - rec["f"]) <= rtol * abs(rec["f"]), f"{f!r} vs the reference's {rec['f']!r}"
