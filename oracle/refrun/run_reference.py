@@ -33,6 +33,7 @@ def load_reference():
     """The reference module, imported from where it lies, with the stand-ins for its two missing dependencies."""
     if not available():
         raise RuntimeError("the reference tree is not present on this machine")
+    sys.dont_write_bytecode = True  # the reference tree is read-only by agreement: no __pycache__ next to its sources
     for p in (os.path.join(HERE, "stubs"), REFERENCE_ROOT):
         if p not in sys.path:
             sys.path.insert(0, p)

@@ -18,7 +18,8 @@ def _run(test_file, tmp_path):
     if not rr.available():
         pytest.skip("reference tree not present")
     env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "oracle", "refrun", "stubs"), rr.REFERENCE_ROOT, ROOT]),
-               OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2", MKL_NUM_THREADS="2")
+               OMP_NUM_THREADS="2", OPENBLAS_NUM_THREADS="2", MKL_NUM_THREADS="2",
+               PYTHONDONTWRITEBYTECODE="1")  # nothing is written next to the reference's sources
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(rr.REFERENCE_ROOT, "tests", test_file), "-q",
                         "-p", "no:cacheprovider", f"--rootdir={tmp_path}"], cwd=tmp_path, env=env, capture_output=True,
                        text=True, timeout=1500)
