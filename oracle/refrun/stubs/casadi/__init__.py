@@ -10,6 +10,11 @@ NLP without solving it.  Scalar operations apply the construction-time simplific
 (``0*x -> 0``, ``x+0 -> x``, ``x-x -> 0``, ``1*x -> x``, ``x*x -> sq(x)`` ...), because the reference's Jacobian pattern
 depends on them (exact-zero table entries disappear from the pattern).
 
+Which CasADi: the reference pins casadi==3.6.0 (requirements.txt:4; >=3.5.5 in setup.py:29); it is third-party, un-vendored
+and absent from /root/reference and from this image.  The call sites served here are mpopt.py:114-128, 152, 177-206,
+228-232, 255-298, 317-321, 360-372, 406-408, 455-458, 484-516, 537-543, 624-627, 757, 804, 873-896, 996-1076, 1307-1344,
+1464-1482, 1512-1573, 3038-3131, 3206, 3243-3268, 3718, 3830-3903, 4000-4062.
+
 What it is not: CasADi.  Values produced through it are the reference's FORMULAS evaluated in IEEE double arithmetic; the
 order of floating-point operations inside ``mtimes`` follows CasADi's (ascending inner index), reverse-mode AD is replaced
 by forward-mode (same numbers up to rounding).  Jacobian sparsity = structural dependence of the simplified graph, which
